@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the b200 back-end (BASELINE.json metric:
+"GB/s & % HBM peak: forall+ReduceSum, inclusive_scan, sort_pairs @2^28, 1-8 GPU").
+
+A "step" is one pass of the hot path over one batch of synthetic input, N = 2^28 per GPU:
+    1. forall + ReduceSum   dot product, fp64            16 B/element  (4.29 GB)
+    2. inclusive_scan       int32, operators::plus        8 B/element  (2.15 GB)
+    3. sort_pairs           uint32 keys + uint32 values  68 B/element  (18.25 GB, onesweep model:
+                            K + P*2*(K+V), P = 4 passes; the 2*(K+V) = 16 B lower bound is reported too)
+`value` = algorithmic bytes of the step / device time of the step, summed over ranks, in GB/s.
+Inputs are resident in HBM before the timed region (every step sorts its own fresh unsorted
+buffers, so nothing is restored inside the region) and each is >= 1 GiB, far larger than the
+126 MB L2.  `e2e` is the same step through the public API from pinned HOST buffers (H2D of all
+inputs, D2H of all results inside the timed region).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--log2n 28] [--impl b200|reference]
+For N > 1 launch with torch.distributed.run (one rank per GPU); rank 0 prints one JSON line.
+--impl reference times the reference's own CPU implementation (oracle/_ref: RAJA
+omp_parallel_for_exec compiled from the reference headers; falls back to the oracle port) on the
+host cores on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "hot-path throughput: forall+ReduceSum(dot f64) + inclusive_scan(i32) + sort_pairs(u32,u32) @2^28 per GPU"
+BYTES_DOT, BYTES_SCAN, BYTES_SORT_MODEL, BYTES_SORT_LOWER = 16, 8, 68, 16
+BYTES_ONESWEEP_PASS = 16  # one onesweep launch: read K+V, write K+V
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                f = [x.strip() for x in line.split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for f in self.samples:
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- reference arm
+def cpu_workload(n, seed=12345):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0.5, 1.5, n)
+    y = rng.uniform(0.5, 1.5, n)
+    s = rng.integers(0, 8, n).astype(np.int32)
+    k = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    v = np.arange(n, dtype=np.uint32)
+    return x, y, s, k, v
+
+
+def cpu_step(ref, data):
+    """one step of the hot path on the host; returns seconds per path"""
+    import numpy as np
+    x, y, s, k, v = data
+    t0 = time.perf_counter()
+    ref.dot(x, y)
+    t_dot = time.perf_counter() - t0
+    scan_fn = ref._fn("inclusive_scan_i32", None, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64])
+    out = np.empty_like(s)
+    t1 = time.perf_counter()
+    scan_fn(0, s.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), s.size)
+    t2 = time.perf_counter()
+    kk, vv = k.copy(), v.copy()
+    if ref.kind == "reference":
+        f = ref._fn("sort_pairs32_u32", None, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int])
+        t3 = time.perf_counter()
+        f(0, kk.ctypes.data_as(ctypes.c_void_p), vv.ctypes.data_as(ctypes.c_void_p), kk.size, 0)  # RAJA::sort_pairs (unstable)
+        t4 = time.perf_counter()
+    else:
+        t3 = time.perf_counter()
+        ref.stable_sort_pairs(k, v)
+        t4 = time.perf_counter()
+    return {"dot": t_dot, "scan": t2 - t1, "sort": t4 - t3}
+
+
+def cpu_reference(log2n, steps, warmup):
+    from oracle_lib import Oracle, Reference
+    if Reference.available():
+        ref = Reference(1)  # omp_parallel_for_exec with every host thread
+        what = "RAJA omp_parallel_for_exec/omp_reduce from oracle/_ref (reference headers, g++ -O2 -fopenmp)"
+    else:
+        ref = Oracle()
+        what = "oracle/liboracle.so (plain-C port, single thread)"
+    n = 1 << log2n
+    data = cpu_workload(n)
+    for _ in range(warmup):
+        cpu_step(ref, data)
+    acc = {"dot": 0.0, "scan": 0.0, "sort": 0.0}
+    for _ in range(steps):
+        for kk, vv in cpu_step(ref, data).items():
+            acc[kk] += vv
+    per = {k: v / steps for k, v in acc.items()}
+    total_bytes = n * (BYTES_DOT + BYTES_SCAN + BYTES_SORT_MODEL)
+    total_s = sum(per.values())
+    paths = {"dot_f64": {"gbs": n * BYTES_DOT / per["dot"] / 1e9, "ms": per["dot"] * 1e3},
+             "inclusive_scan_i32": {"gbs": n * BYTES_SCAN / per["scan"] / 1e9, "ms": per["scan"] * 1e3},
+             "sort_pairs_u32": {"gbs_model": n * BYTES_SORT_MODEL / per["sort"] / 1e9, "ms": per["sort"] * 1e3,
+                                "mpairs_s": n / per["sort"] / 1e6}}
+    return {"value": total_bytes / total_s / 1e9, "ms_per_step": total_s * 1e3, "cores": ref.cores, "kind": ref.kind,
+            "sample": f"same 3-path step at N=2^{log2n} per path ({what}); GB/s uses the same algorithmic bytes/element",
+            "paths": paths}
+
+
+# --------------------------------------------------------------------------------------- b200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 back-end has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import raja_b200 as rb
+    from raja_b200._lib import lib
+    rbm = None
+    if world > 1:
+        from raja_b200 import multi as rbm
+
+    n = 1 << args.log2n
+    K, W = args.steps, max(args.warmup, 3)
+    dev = torch.device("cuda", local)
+    g = torch.Generator(device=dev).manual_seed(12345 + rank)
+
+    # ---- inputs resident in HBM before the timed region
+    x = torch.rand(n, dtype=torch.float64, device=dev, generator=g) + 0.5
+    y = torch.rand(n, dtype=torch.float64, device=dev, generator=g) + 0.5
+    s_in = torch.randint(0, 8, (n,), dtype=torch.int32, device=dev, generator=g)
+    s_out = torch.empty_like(s_in)
+    nsets = K + W
+    sort_sets = []
+    for i in range(nsets):
+        k = torch.randint(-2**31, 2**31, (n,), dtype=torch.int64, device=dev, generator=g).to(torch.int32).view(torch.uint32)
+        v = torch.arange(n, dtype=torch.int32, device=dev).view(torch.uint32)
+        sort_sets.append((k, v))
+    k_alt = torch.empty(n, dtype=torch.int32, device=dev).view(torch.uint32)
+    v_alt = torch.empty(n, dtype=torch.int32, device=dev).view(torch.uint32)
+    sharded = rbm.ShardedRange(world, rank) if world > 1 else None
+
+    stream = torch.cuda.current_stream()
+    res = rb.Resource(stream)
+    apol = rb.b200_exec(async_=True)
+    dot_out = rb.PinnedBuffer(16)
+
+    def step(i, ev=None):
+        k, v = sort_sets[i]
+        if ev: ev[0].record(stream)
+        if sharded:
+            rbm.reduce_dot(sharded, x, y, res=res)
+        else:
+            rb._lib.check(lib.rb200_reduce_dot(rb._lib.F64, x.data_ptr(), y.data_ptr(), n, dot_out.ptr, res.handle), "dot")
+        if ev: ev[1].record(stream)
+        if sharded:
+            rbm.inclusive_scan(sharded, s_in, s_out, res=res)
+        else:
+            rb.inclusive_scan(s_in, s_out, pol=apol, res=res)
+        if ev: ev[2].record(stream)
+        if sharded:
+            rbm.sort_pairs(sharded, k, v, res=res, keys_alt=k_alt, vals_alt=v_alt)
+        else:
+            rb.sort_pairs(k, v, pol=apol, res=res, keys_alt=k_alt, vals_alt=v_alt)
+        if ev: ev[3].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i)
+    barrier()
+
+    lib.rb200_profile_reset()
+    lib.rb200_profile_enable(1)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler: sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        step(W + i, evs[i])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.finish() if sampler else None
+    launches = lib.rb200_launch_count()
+    lib.rb200_profile_enable(0)
+
+    ms = {"dot": 0.0, "scan": 0.0, "sort": 0.0}
+    for e in evs:
+        ms["dot"] += e[0].elapsed_time(e[1])
+        ms["scan"] += e[1].elapsed_time(e[2])
+        ms["sort"] += e[2].elapsed_time(e[3])
+    ms = {k: v / K for k, v in ms.items()}
+    step_ms = sum(ms.values())
+    t = torch.tensor([step_ms, ms["dot"], ms["scan"], ms["sort"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, dot_ms, scan_ms, sort_ms = t.tolist()
+
+    # dominant kernel (onesweep pass) timed live with CUDA events on the launching stream
+    tot, cnt = ctypes.c_double(), ctypes.c_longlong()
+    lib.rb200_profile_query(b"onesweep_kernel", ctypes.byref(tot), ctypes.byref(cnt))
+    pass_ms = tot.value / max(cnt.value, 1)
+    kern = {}
+    for name in (b"forall_reduce_kernel", b"scan_kernel", b"histogram_kernel", b"onesweep_kernel"):
+        lib.rb200_profile_query(name, ctypes.byref(tot), ctypes.byref(cnt))
+        kern[name.decode()] = {"launches": cnt.value, "avg_ms": tot.value / max(cnt.value, 1), "share_of_step": tot.value / K / step_ms if step_ms else None}
+
+    # ---- e2e: same step from pinned host buffers through the public API
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(rb, rbm, sharded, n, dev, stream, res, world, barrier, min(K, args.e2e_steps))
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    bytes_step = n * (BYTES_DOT + BYTES_SCAN + BYTES_SORT_MODEL)
+    value = world * bytes_step / (step_ms * 1e-3) / 1e9
+    paths = {
+        "forall_reducesum_dot_f64": {"ms": dot_ms, "gbs": n * BYTES_DOT / dot_ms / 1e6, "frac_hbm": n * BYTES_DOT / dot_ms / 1e6 / peak},
+        "inclusive_scan_i32": {"ms": scan_ms, "gbs": n * BYTES_SCAN / scan_ms / 1e6, "frac_hbm": n * BYTES_SCAN / scan_ms / 1e6 / peak},
+        "sort_pairs_u32_u32": {"ms": sort_ms, "gbs_model68": n * BYTES_SORT_MODEL / sort_ms / 1e6, "frac_hbm_model68": n * BYTES_SORT_MODEL / sort_ms / 1e6 / peak,
+                               "gbs_lower16": n * BYTES_SORT_LOWER / sort_ms / 1e6, "gpairs_s": n / sort_ms / 1e6},
+    }
+    achieved = n * BYTES_ONESWEEP_PASS / pass_ms / 1e6 if pass_ms else None
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        c = cpu_reference(args.cpu_log2n, 2, 1)
+        cpu = {"value": c["value"], "unit": "GB/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"], "paths": c["paths"]}
+    line = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32+u32", "data": "synthetic",
+        "config": {"workload": f"dot(f64)+inclusive_scan(i32)+sort_pairs(u32,u32), N=2^{args.log2n} elements per path per GPU",
+                   "l2": "inputs (1-2 GiB each) larger than the 126 MB L2; every step sorts fresh unsorted buffers",
+                   "sharding": "none" if world == 1 else "contiguous shards; allreduce(dot), carry allgather(scan), sample-sort all-to-all(sort)"},
+        "paths": paths,
+        "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (one radix pass, u32 keys + u32 values)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_launch": n * BYTES_ONESWEEP_PASS, "avg_launch_ms": pass_ms},
+        "kernels": kern,
+        "cpu_baseline": cpu,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "wall_ms_per_step": t_wall * 1e3 / K,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
+def run_e2e(rb, rbm, sharded, n, dev, stream, res, world, barrier, steps):
+    import torch
+    import torch.distributed as dist
+    g = torch.Generator().manual_seed(7)
+    hx = torch.empty(n, dtype=torch.float64).pin_memory()
+    hy = torch.empty(n, dtype=torch.float64).pin_memory()
+    hs = torch.empty(n, dtype=torch.int32).pin_memory()
+    hk = torch.empty(n, dtype=torch.int32).pin_memory()
+    hv = torch.empty(n, dtype=torch.int32).pin_memory()
+    hx.uniform_(0.5, 1.5, generator=g); hy.uniform_(0.5, 1.5, generator=g)
+    hs.random_(0, 8, generator=g); hk.random_(-2**31, 2**31 - 1, generator=g)
+    hv.copy_(torch.arange(n, dtype=torch.int32))
+    ho_s = torch.empty(n, dtype=torch.int32).pin_memory()
+    ho_k = torch.empty(n, dtype=torch.int32).pin_memory()
+    ho_v = torch.empty(n, dtype=torch.int32).pin_memory()
+    dx = torch.empty(n, dtype=torch.float64, device=dev); dy = torch.empty_like(dx)
+    ds = torch.empty(n, dtype=torch.int32, device=dev); dso = torch.empty_like(ds)
+    dk = torch.empty(n, dtype=torch.int32, device=dev); dv = torch.empty_like(dk)
+    ka = torch.empty_like(dk); va = torch.empty_like(dk)
+    apol = rb.b200_exec(async_=True)
+
+    def one():
+        dx.copy_(hx, non_blocking=True); dy.copy_(hy, non_blocking=True)
+        d = rbm.reduce_dot(sharded, dx, dy, res=res) if sharded else rb.reduce_dot(dx, dy, res=res)  # reads the scalar back
+        ds.copy_(hs, non_blocking=True)
+        if sharded: rbm.inclusive_scan(sharded, ds, dso, res=res)
+        else: rb.inclusive_scan(ds, dso, pol=apol, res=res)
+        ho_s.copy_(dso, non_blocking=True)
+        dk.copy_(hk, non_blocking=True); dv.copy_(hv, non_blocking=True)
+        ku, vu = dk.view(torch.uint32), dv.view(torch.uint32)
+        if sharded: rbm.sort_pairs(sharded, ku, vu, res=res, keys_alt=ka.view(torch.uint32), vals_alt=va.view(torch.uint32))
+        else: rb.sort_pairs(ku, vu, pol=apol, res=res, keys_alt=ka.view(torch.uint32), vals_alt=va.view(torch.uint32))
+        ho_k.copy_(dk, non_blocking=True); ho_v.copy_(dv, non_blocking=True)
+        return d
+
+    one()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        one()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    h2d = n * (8 + 8 + 4 + 4 + 4)
+    d2h = n * (4 + 4 + 4) + 8
+    return {"value": world * n * (BYTES_DOT + BYTES_SCAN + BYTES_SORT_MODEL) / (ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms,
+            "steps": steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "note": "pinned host -> device copies of x,y,scan input,keys,vals and device -> host of scan output, sorted keys+vals, dot scalar, all inside the timed region"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    c = cpu_reference(args.cpu_log2n, max(args.steps, 1), max(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": c["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": c["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32+u32",
+            "data": "synthetic",
+            "config": {"workload": f"dot(f64)+inclusive_scan(i32)+sort_pairs(u32,u32), bounded sample N=2^{args.cpu_log2n} per path on the host cores"},
+            "paths": c["paths"],
+            "cpu_baseline": {"value": c["value"], "unit": "GB/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"]},
+            "e2e": {"value": c["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--log2n", type=int, default=28)
+    ap.add_argument("--cpu-log2n", type=int, default=24)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

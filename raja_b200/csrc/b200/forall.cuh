@@ -1,0 +1,139 @@
+// raja_b200 core: the forall engine.
+//
+// Replaces the reference's four forallp_cuda_kernel variants and their
+// dimension calculators (policy/cuda/forall.hpp:73-353, 383-542;
+// MemUtils_CUDA.hpp:527-613) with ONE mapping: a persistent grid
+// (SMs x resident CTAs) that walks tiles of BLOCK*UNROLL indices round-robin.
+// Inside a tile the UNROLL bodies of a thread are BLOCK apart, so every load a
+// body issues is a fully coalesced warp access and UNROLL of them are in flight
+// per thread (B200 needs ~30-40 KB outstanding per SM to saturate HBM3e).
+//
+// Body is copied into each thread (the reference's thread_privatize,
+// pattern/detail/privatizer.hpp:45-99): it may carry per-thread state such as
+// reduction accumulators.  After the loop `fin(body)` runs once per thread; that
+// is where block/grid reductions happen.
+#pragma once
+#include "common.cuh"
+#include "reduce.cuh"
+
+namespace b200 {
+
+struct NoFinalize {
+  template <class Body> B200_D void operator()(Body&) const {}
+};
+
+// Optional body hooks, detected at compile time:
+//   template <int U> void tile(Index base, Index stride)
+//        -- process indices base + u*stride, u in [0,U), in one call, so the body
+//           can issue all of its loads before its first store (an opaque
+//           operator() cannot be reordered across stores that may alias);
+//   Index tail_len() const / void tail(Index j)
+//        -- j in [0, tail_len()): scalar leftovers of a vectorised index space,
+//           run once by one block after the main loop.
+namespace detail {
+template <class Body, class Index, int U, class = void> struct has_tile : std::false_type {};
+template <class Body, class Index, int U>
+struct has_tile<Body, Index, U, std::void_t<decltype(std::declval<Body&>().template tile<U>(std::declval<Index>(), std::declval<Index>()))>>
+    : std::true_type {};
+template <class Body, class Index, class = void> struct has_tail : std::false_type {};
+template <class Body, class Index>
+struct has_tail<Body, Index, std::void_t<decltype(std::declval<Body&>().tail(std::declval<Index>()))>> : std::true_type {};
+}  // namespace detail
+
+template <int BLOCK, int UNROLL, class Index, class Body, class Finalize>
+__global__ void __launch_bounds__(BLOCK)
+forall_kernel(const __grid_constant__ Body body_in, const Index len, const __grid_constant__ Finalize fin)
+{
+  Body body = body_in;
+  constexpr Index TILE = Index(BLOCK) * UNROLL;
+  const Index full_tiles = len / TILE;
+  for (Index t = blockIdx.x; t < full_tiles; t += gridDim.x) {
+    const Index base = t * TILE + threadIdx.x;
+    if constexpr (detail::has_tile<Body, Index, UNROLL>::value) {
+      body.template tile<UNROLL>(base, Index(BLOCK));
+    } else {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) body(base + Index(u) * BLOCK);
+    }
+  }
+  // ragged last tile (< TILE indices): given to the block that would own the next tile
+  if (blockIdx.x == (unsigned)(full_tiles % gridDim.x)) {
+    for (Index i = full_tiles * TILE + threadIdx.x; i < len; i += BLOCK) body(i);
+  }
+  if constexpr (detail::has_tail<Body, Index>::value) {
+    if (blockIdx.x == gridDim.x - 1) {
+      for (Index j = threadIdx.x; j < body.tail_len(); j += BLOCK) body.tail(j);
+    }
+  }
+  fin(body);
+}
+
+// Grid size for the persistent mapping: every SM gets its resident CTAs, never
+// more blocks than tiles.
+inline int persistent_grid(int occ_per_sm, long long tiles)
+{
+  long long g = (long long)device_info().sm_count * (occ_per_sm > 0 ? occ_per_sm : 1);
+  if (tiles < 1) tiles = 1;
+  if (g > tiles) g = tiles;
+  return (int)g;
+}
+
+template <int BLOCK, int UNROLL, class Index, class Body, class Finalize>
+inline int forall_occupancy()
+{
+  // occupancy is a property of the instantiation; query once per host thread
+  static thread_local int cached = 0;
+  if (cached == 0) {
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, forall_kernel<BLOCK, UNROLL, Index, Body, Finalize>, BLOCK, 0);
+    cached = occ > 0 ? occ : 1;
+  }
+  return cached;
+}
+
+template <int BLOCK, int UNROLL, class Index, class Body, class Finalize>
+inline int forall_grid(Index len)
+{
+  long long tiles = ((long long)len + (long long)BLOCK * UNROLL - 1) / ((long long)BLOCK * UNROLL);
+  return persistent_grid(forall_occupancy<BLOCK, UNROLL, Index, Body, Finalize>(), tiles);
+}
+
+template <int BLOCK, int UNROLL, class Index, class Body, class Finalize>
+inline cudaError_t launch_forall(cudaStream_t stream, const Body& body, Index len, const Finalize& fin, int grid,
+                                 const char* name = "forall_kernel")
+{
+  LaunchScope scope(name, stream);
+  if (len < 0) return cudaErrorInvalidValue;  // len == 0 still launches: the body may own tail work
+  forall_kernel<BLOCK, UNROLL, Index, Body, Finalize><<<grid, BLOCK, 0, stream>>>(body, len, fin);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Reduction finalizer: folds the per-thread accumulator `body.acc` across the
+// block and the grid and lets the last block write the result.
+//   ordered == true : last-block-done, fixed slot order (deterministic)
+//   ordered == false: one atomic per block on *out (out must hold the identity
+//                     or a running value beforehand)
+// ---------------------------------------------------------------------------
+template <int BLOCK, class Op, bool Ordered = true> struct ReduceFinalize {
+  using T = typename Op::value_type;
+  T* partials;        // [grid]
+  unsigned* counter;  // zero on entry, zero on exit
+  T* out;             // device-accessible result slot
+  template <class Body> B200_D void operator()(Body& body) const
+  {
+    __shared__ T smem[32];
+    Op op;
+    T v = block_reduce<BLOCK>(body.acc, op, smem);
+    if constexpr (Ordered) {
+      T r;
+      if (grid_combine_last_block<BLOCK>(v, op, partials, counter, smem, r)) {
+        if (threadIdx.x == 0) *out = r;
+      }
+    } else {
+      if (threadIdx.x == 0) atomic_combine(op, out, v);
+    }
+  }
+};
+
+}  // namespace b200

@@ -1,0 +1,291 @@
+// raja_b200 runtime: error state and the stream-ordered pools.
+//
+// Replaces the reference's process-wide first-fit arena pools
+// (util/basic_mempool.hpp:302-430 instantiated by policy/cuda/MemUtils_CUDA.hpp:69-167,
+// globals in src/MemUtils_CUDA.cpp:43-53).  Design: one size-keyed free list per
+// (device, stream).  A block freed on stream S is only reused by later allocations
+// on S, so "free right after enqueue" -- what the reference's scan/sort do
+// (policy/cuda/scan.hpp:81, sort.hpp:142,152) -- is safe by construction instead of
+// by luck.  Pinned blocks are not stream-keyed (the host owns their lifetime).
+#include "runtime.hpp"
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+#include <cstdio>
+
+namespace rb200 {
+
+static thread_local std::string tl_error;
+
+void set_error(const std::string& msg) { tl_error = msg; }
+int fail(int code, const char* what)
+{
+  tl_error = what;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what)
+{
+  tl_error = std::string(what) + ": " + cudaGetErrorString(e);
+  cudaGetLastError();  // clear sticky-free errors
+  return (int)e;
+}
+
+namespace {
+
+struct Block {
+  size_t bytes;
+  PoolKind kind;
+  int device;
+};
+
+struct Pools {
+  std::mutex mu;
+  // live + cached blocks: ptr -> info
+  std::unordered_map<void*, Block> blocks;
+  // free lists keyed by (kind, device, stream) -> size -> ptrs
+  struct Key {
+    int kind, device;
+    cudaStream_t stream;
+    bool operator<(const Key& o) const
+    {
+      if (kind != o.kind) return kind < o.kind;
+      if (device != o.device) return device < o.device;
+      return stream < o.stream;
+    }
+  };
+  std::map<Key, std::multimap<size_t, void*>> free_lists;
+  size_t cached_bytes = 0;
+};
+
+Pools& pools()
+{
+  static Pools* p = new Pools();  // leaked on purpose: outlives CUDA teardown order problems
+  return *p;
+}
+
+size_t round_size(size_t bytes)
+{
+  if (bytes < 512) return 512;
+  // 1/8-octave size classes bound internal waste to 12.5 % while letting near-equal
+  // requests (scan/sort workspaces of successive calls) share blocks
+  size_t p2 = 512;
+  while (p2 * 2 <= bytes) p2 *= 2;
+  size_t step = p2 / 8;
+  return ((bytes + step - 1) / step) * step;
+}
+
+}  // namespace
+
+void* pool_malloc(PoolKind kind, size_t bytes, cudaStream_t stream)
+{
+  if (bytes == 0) bytes = 1;
+  const size_t want = round_size(bytes);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  Pools& P = pools();
+  Pools::Key key{(int)kind, dev, kind == POOL_PINNED ? (cudaStream_t)0 : stream};
+  {
+    std::lock_guard<std::mutex> g(P.mu);
+    auto fl = P.free_lists.find(key);
+    if (fl != P.free_lists.end()) {
+      auto it = fl->second.lower_bound(want);
+      if (it != fl->second.end() && it->first <= want + want / 4) {
+        void* p = it->second;
+        P.cached_bytes -= it->first;
+        fl->second.erase(it);
+        return p;
+      }
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e;
+  if (kind == POOL_PINNED) {
+    e = cudaHostAlloc(&p, want, cudaHostAllocMapped | cudaHostAllocPortable);
+  } else {
+    e = cudaMalloc(&p, want);
+    if (e == cudaErrorMemoryAllocation) {
+      // give cached blocks back to the driver and retry once
+      cudaGetLastError();
+      rb200_pool_trim();
+      e = cudaMalloc(&p, want);
+    }
+    if (e == cudaSuccess && kind == POOL_DEVICE_ZEROED) {
+      e = cudaMemsetAsync(p, 0, want, stream);
+    }
+  }
+  if (e != cudaSuccess) {
+    cuda_fail(e, "pool allocation");
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> g(P.mu);
+  P.blocks[p] = Block{want, kind, dev};
+  return p;
+}
+
+int pool_free(PoolKind kind, void* p, cudaStream_t stream)
+{
+  if (!p) return 0;
+  Pools& P = pools();
+  std::lock_guard<std::mutex> g(P.mu);
+  auto it = P.blocks.find(p);
+  if (it == P.blocks.end() || it->second.kind != kind) return fail(RB200_EINVAL, "pool_free: pointer does not belong to this pool");
+  Pools::Key key{(int)kind, it->second.device, kind == POOL_PINNED ? (cudaStream_t)0 : stream};
+  P.free_lists[key].emplace(it->second.bytes, p);
+  P.cached_bytes += it->second.bytes;
+  return 0;
+}
+
+}  // namespace rb200
+
+// ---------------------------------------------------------------------------
+// launch accounting: installed as the core's LaunchHook at load time
+// ---------------------------------------------------------------------------
+#include "b200/common.cuh"
+#include <atomic>
+#include <cstring>
+
+namespace rb200 {
+namespace {
+struct LaunchRecord {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_profile{0};
+std::mutex g_prof_mu;
+std::vector<LaunchRecord> g_records;
+thread_local cudaEvent_t tl_e1 = nullptr;
+
+void hook_begin(const char* name, cudaStream_t stream)
+{
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  tl_e1 = nullptr;
+  if (!g_profile.load(std::memory_order_relaxed)) return;
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return;
+  cudaEventRecord(e0, stream);
+  tl_e1 = e1;
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  if (g_records.size() < (1u << 20)) g_records.push_back({name, e0, e1});
+}
+void hook_end(const char*, cudaStream_t stream)
+{
+  if (tl_e1) cudaEventRecord(tl_e1, stream);
+  tl_e1 = nullptr;
+}
+struct HookInstaller {
+  HookInstaller()
+  {
+    b200::launch_hook().begin = hook_begin;
+    b200::launch_hook().end = hook_end;
+  }
+} g_hook_installer;
+}  // namespace
+}  // namespace rb200
+
+using namespace rb200;
+
+extern "C" {
+
+long long rb200_launch_count(void) { return g_launches.load(); }
+int rb200_profile_enable(int on)
+{
+  g_profile.store(on ? 1 : 0);
+  return 0;
+}
+int rb200_profile_reset(void)
+{
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  for (auto& r : g_records) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_records.clear();
+  g_launches.store(0);
+  return 0;
+}
+int rb200_profile_query(const char* kernel, double* total_ms, long long* launches)
+{
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  double ms = 0;
+  long long cnt = 0;
+  for (auto& r : g_records) {
+    if (kernel && std::strcmp(kernel, r.name) != 0) continue;
+    RB200_CUDA(cudaEventSynchronize(r.e1));
+    float t = 0;
+    RB200_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms += t;
+    ++cnt;
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = cnt;
+  return 0;
+}
+
+int rb200_version(void) { return RB200_VERSION; }
+const char* rb200_last_error(void) { return tl_error.c_str(); }
+
+int rb200_sm_count(void)
+{
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+int rb200_stream_synchronize(rb200_stream_t stream)
+{
+  RB200_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+int rb200_device_synchronize(void)
+{
+  RB200_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+void* rb200_device_malloc(size_t bytes, rb200_stream_t s) { return pool_malloc(POOL_DEVICE, bytes, (cudaStream_t)s); }
+void* rb200_device_zeroed_malloc(size_t bytes, rb200_stream_t s) { return pool_malloc(POOL_DEVICE_ZEROED, bytes, (cudaStream_t)s); }
+void* rb200_pinned_malloc(size_t bytes) { return pool_malloc(POOL_PINNED, bytes, 0); }
+int rb200_device_free(void* p, rb200_stream_t s) { return pool_free(POOL_DEVICE, p, (cudaStream_t)s); }
+int rb200_device_zeroed_free(void* p, rb200_stream_t s) { return pool_free(POOL_DEVICE_ZEROED, p, (cudaStream_t)s); }
+int rb200_pinned_free(void* p) { return pool_free(POOL_PINNED, p, 0); }
+
+int rb200_pool_trim(void)
+{
+  Pools& P = pools();
+  std::vector<std::pair<void*, Block>> victims;
+  {
+    std::lock_guard<std::mutex> g(P.mu);
+    for (auto& fl : P.free_lists) {
+      for (auto& kv : fl.second) {
+        auto it = P.blocks.find(kv.second);
+        if (it != P.blocks.end()) {
+          victims.emplace_back(kv.second, it->second);
+          P.blocks.erase(it);
+        }
+      }
+      fl.second.clear();
+    }
+    P.cached_bytes = 0;
+  }
+  if (victims.empty()) return 0;
+  // cached blocks may still be referenced by enqueued work
+  cudaDeviceSynchronize();
+  int rc = 0;
+  for (auto& v : victims) {
+    cudaError_t e = (v.second.kind == POOL_PINNED) ? cudaFreeHost(v.first) : cudaFree(v.first);
+    if (e != cudaSuccess) rc = cuda_fail(e, "pool trim");
+  }
+  return rc;
+}
+
+size_t rb200_pool_bytes_cached(void)
+{
+  Pools& P = pools();
+  std::lock_guard<std::mutex> g(P.mu);
+  return P.cached_bytes;
+}
+
+}  // extern "C"
