@@ -333,7 +333,6 @@ def test_atomic_histogram_and_pi(rb, orc, aggregate):
         hist = torch.zeros(256, dtype=dt, device="cuda")
         rb.atomic_histogram(hist, dev(keys), aggregate)
         assert np.array_equal(host(hist).astype(np.int64), np.bincount(keys, minlength=256))
-    assert np.array_equal(host(hist).astype(np.int64), G["hist_256"] * 0 + np.bincount(keys, minlength=256))
     hist = torch.zeros(256, dtype=torch.int32, device="cuda")
     rb.atomic_histogram(hist, dev(G["hist_keys"]), aggregate)
     assert np.array_equal(host(hist), G["hist_256"])
@@ -400,8 +399,8 @@ def test_full_size_reduce_and_scan_properties(rb):
 
 def test_full_size_sort_pairs_properties(rb):
     g = torch.Generator(device="cuda").manual_seed(42)
-    keys = torch.randint(-2**31, 2**31, (N_FULL,), dtype=torch.int64, device="cuda", generator=g).to(torch.int32).view(torch.uint32)
-    keys &= 0xFFFFF  # 2^20 distinct keys -> ~256 duplicates each: stability is observable
+    # 2^20 distinct keys -> ~256 duplicates each: stability is observable
+    keys = torch.randint(0, 1 << 20, (N_FULL,), dtype=torch.int32, device="cuda", generator=g).view(torch.uint32)
     orig = keys.clone()
     vals = torch.arange(N_FULL, dtype=torch.int32, device="cuda").view(torch.uint32)
     rb.sort_pairs(keys, vals)

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Summarise SASS of one kernel in libraja_b200.so: tools_sass.py <regex> [maxlines]"""
 import re, subprocess, sys
-so = 'raja_b200/lib/libraja_b200.so'
+import os
+so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'raja_b200/lib/libraja_b200.so')
 txt = subprocess.run(['cuobjdump', '-sass', so], capture_output=True, text=True).stdout
 funcs = re.split(r'\n\s*Function : ', txt)
 pat = sys.argv[1]; maxlines = int(sys.argv[2]) if len(sys.argv) > 2 else 60
