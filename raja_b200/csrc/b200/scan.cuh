@@ -1,16 +1,42 @@
-// raja_b200 core: single-pass prefix scan with decoupled look-back.
+// raja_b200 core: single-pass prefix scan -- persistent CTAs, TMA bulk staging,
+// early aggregates, full-round decoupled look-back.
 //
 // Replaces the reference's policy/cuda/scan.hpp:52-235 (four entry points that
-// each delegate to cub::DeviceScan).  One kernel reads N and writes N:
-//   * tiles are claimed through an atomic ticket, so a tile's predecessors are
-//     always resident or finished (forward progress without relying on blockIdx
-//     scheduling order);
-//   * data stays in registers in a warp-striped vector layout (lane l of warp w
-//     owns V consecutive items at row k): loads and stores are 128-bit and fully
-//     coalesced with no shared-memory transpose; the in-warp scan costs K
-//     shuffle scans per thread, which is noise next to the HBM time;
-//   * tile status + value travel in one 64-bit word for 4-byte T; 8-byte T uses
-//     separate value arrays published with st.release / read with ld.acquire;
+// each delegate to cub::DeviceScan).  One kernel reads N and writes N.
+//
+//   * persistent grid (SMs x resident CTAs); a CTA takes a virtual id from an
+//     atomic ticket and then owns tiles vid, vid+G, vid+2G, ...  A CTA that holds
+//     virtual id v was started after every id < v, and each CTA works through its
+//     tiles in ascending order, so the lowest unfinished tile is always being
+//     worked on: look-back cannot deadlock whatever the block scheduler does;
+//   * each tile is brought into shared memory by ONE bulk async copy
+//     (cp.async.bulk global->shared, completion on an mbarrier) issued three tiles
+//     ahead, and leaves through ONE bulk async copy shared->global: without the
+//     look-back this pipeline alone streams at ~95 % of a device memcpy
+//     (profiles/r01_scan_tuning.txt);
+//   * in shared memory a thread owns VPT consecutive 16-byte vectors (VPT odd: the
+//     128-bit accesses are bank-conflict free);
+//   * the look-back is what bounds a chained scan on this part: under a saturated
+//     HBM pipe a publish -> observe hop through L2 costs microseconds, and the
+//     classic formulation (publish aggregate, then walk back 32 tiles per hop,
+//     everybody waiting at a barrier) exposes several hops per tile (v1: 68 % of
+//     warp samples at that barrier, 45 % of HBM peak).  Here the chain is taken
+//     off the critical path altogether.  A CTA is BLOCK compute threads plus one
+//     LOOK-BACK WARP, and iteration i of a CTA runs
+//       compute warps : reduce tile i+2 and publish its aggregate (two iterations
+//                       early), then scan tile i with its already-known prefix;
+//       look-back warp: prefix(i+1) = inclusive(own tile i-1)
+//                                     (+) aggregates of the 2G-1 tiles in between,
+//                       fetched in ONE batch of loads (G = grid size), and the
+//                       bulk copies.
+//     Every aggregate the look-back warp needs was published a full iteration
+//     before it asks, and its answer is not needed until the next iteration, so
+//     neither the store nor the load latency is ever waited for; there are no
+//     "inclusive" states at all, the fold order is fixed, and floating-point
+//     scans are therefore run-to-run deterministic (CUB's are not);
+//   * a tile's "published" flag + aggregate travel in one 64-bit word for 4-byte T;
+//     an 8-byte T is split into two such words (flag + low half, flag + high half)
+//     and is valid when both flags are set, so no acquire/release chain is needed;
 //   * 64-bit lengths (the reference truncates to int: scan.hpp:65).
 //
 // Semantics follow the reference's sequential definition
@@ -20,252 +46,377 @@
 #pragma once
 #include "common.cuh"
 #include "reduce.cuh"
+#include "tma.cuh"
 
 namespace b200 {
 namespace scan {
 
-enum : uint32_t { TS_INVALID = 0, TS_AGGREGATE = 1, TS_INCLUSIVE = 2 };
-
 template <class T, bool Packed = (sizeof(T) == 4)> struct TileState;
 
+// 4-byte T: one 64-bit word per tile, (1 << 32 | aggregate); zero = not published.
 template <class T> struct TileState<T, true> {
   uint64_t* words;
   static size_t bytes(long long ntiles) { return (size_t)ntiles * 8; }
   void bind(void* base, long long) { words = (uint64_t*)base; }
-  B200_D void publish(long long tile, uint32_t status, T v) const
+  B200_D void publish(long long tile, T v) const
   {
     uint32_t bits;
     memcpy(&bits, &v, 4);
-    st_relaxed_u64(words + tile, ((uint64_t)status << 32) | bits);
+    st_relaxed_u64(words + tile, (1ull << 32) | bits);
   }
-  B200_D uint32_t peek(long long tile, T& v) const
+  B200_D bool peek(long long tile, T& v) const
   {
-    uint64_t w = ld_relaxed_u64(words + tile);
-    uint32_t bits = (uint32_t)w;
+    const uint64_t w = ld_relaxed_u64(words + tile);
+    const uint32_t bits = (uint32_t)w;
     memcpy(&v, &bits, 4);
-    return (uint32_t)(w >> 32);
+    return (w >> 32) != 0;
   }
 };
 
+// 8-byte T: two 64-bit words per tile, each (1 << 32 | half of the aggregate).  Each word
+// is written once, so the value is complete exactly when both flags are set -- a torn
+// observation just reads as "not published yet".
 template <class T> struct TileState<T, false> {
   static_assert(sizeof(T) == 8, "scan supports 4- and 8-byte types");
-  uint32_t* status;
-  uint64_t* agg;
-  uint64_t* incl;
-  static size_t bytes(long long ntiles)
-  {
-    size_t st = ((size_t)ntiles * 4 + 127) & ~size_t(127);
-    return st + (size_t)ntiles * 16;
-  }
-  void bind(void* base, long long ntiles)
-  {
-    size_t st = ((size_t)ntiles * 4 + 127) & ~size_t(127);
-    status = (uint32_t*)base;
-    agg = (uint64_t*)((char*)base + st);
-    incl = agg + ntiles;
-  }
-  B200_D void publish(long long tile, uint32_t s, T v) const
+  uint64_t* words;  // [ntiles][2], 16-byte aligned
+  static size_t bytes(long long ntiles) { return (size_t)ntiles * 16; }
+  void bind(void* base, long long) { words = (uint64_t*)base; }
+  B200_D void publish(long long tile, T v) const
   {
     uint64_t bits;
     memcpy(&bits, &v, 8);
-    st_relaxed_u64((s == TS_AGGREGATE ? agg : incl) + tile, bits);
-    st_release_u32(status + tile, s);
+    const uint64_t lo = (1ull << 32) | (bits & 0xffffffffull);
+    const uint64_t hi = (1ull << 32) | (bits >> 32);
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(words + 2 * tile), "l"(lo), "l"(hi) : "memory");
   }
-  B200_D uint32_t peek(long long tile, T& v) const
+  B200_D bool peek(long long tile, T& v) const
   {
-    uint32_t s = ld_acquire_u32(status + tile);
-    if (s != TS_INVALID) {
-      uint64_t bits = ld_relaxed_u64((s == TS_AGGREGATE ? agg : incl) + tile);
-      memcpy(&v, &bits, 8);
-    }
-    return s;
+    uint64_t lo, hi;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(words + 2 * tile) : "memory");
+    const uint64_t bits = (hi << 32) | (lo & 0xffffffffull);
+    memcpy(&v, &bits, 8);
+    return ((lo >> 32) & (hi >> 32)) != 0;
   }
 };
 
-// BLOCK threads, each owning K rows of V consecutive items.
-template <class T, class Op, bool Inclusive, int BLOCK, int K, int V>
-__global__ void __launch_bounds__(BLOCK)
-scan_kernel(const T* in, T* out, const long long n, const T init, const TileState<T> ts, unsigned* ticket)
+// Compile-time shape of one scan kernel.
+//   BLOCK  compute threads per CTA (the CTA has BLOCK + 32 threads)
+//   VPT    16-byte vectors per thread (odd => conflict-free LDS.128/STS.128)
+//   ROWS   look-back batch = ROWS*32 predecessor aggregates per lane-row; the launcher
+//          keeps 2*grid - 1 <= ROWS*32
+//   SLOTS  shared-memory tile slots; LAG = how many outgoing copies may still be reading
+//          their slot when the next load is issued.  Tile i+2 is reduced while tile i is
+//          scanned, so SLOTS >= 4 + LAG; loads run SLOTS-1-LAG tiles ahead of the scan.
+template <int BLOCK_, int VPT_, int ROWS_, int SLOTS_ = 4, int LAG_ = 0> struct Shape {
+  static constexpr int BLOCK = BLOCK_, VPT = VPT_, ROWS = ROWS_, SLOTS = SLOTS_, LAG = LAG_;
+  static constexpr int THREADS = BLOCK + WARP;
+  static constexpr int AHEAD = SLOTS - 1 - LAG;
+  static_assert(BLOCK % WARP == 0 && BLOCK + WARP <= 1024, "");
+  static_assert(SLOTS >= 4 + LAG, "");
+};
+
+template <class T, class S> struct Layout {
+  static constexpr int V = 16 / sizeof(T);
+  static constexpr int ITEMS = S::VPT * V;
+  static constexpr int TILE = S::BLOCK * ITEMS;
+  static constexpr unsigned TILE_BYTES = TILE * sizeof(T);
+  static constexpr int NW = S::BLOCK / WARP;
+  // [SLOTS tiles][SLOTS mbarriers][3 x 32 warp totals][2 prefixes][vid]
+  static constexpr size_t OFF_BAR = (size_t)S::SLOTS * TILE_BYTES;
+  static constexpr size_t OFF_WARP = OFF_BAR + 8 * S::SLOTS;
+  static constexpr size_t OFF_PREFIX = OFF_WARP + 3 * 8 * 32;
+  static constexpr size_t OFF_VID = OFF_PREFIX + 16;
+  static constexpr size_t SMEM_BYTES = OFF_VID + 8;
+};
+
+enum : int { F_BULK_IN = 1, F_BULK_OUT = 2,  // pointer is 16-byte aligned: bulk copies allowed
+              F_DBG_NO_LOOKBACK = 4 };        // tools/tune only: timing experiment (wrong results)
+
+template <int COUNT> B200_D void named_barrier_1() { asm volatile("bar.sync 1, %0;" ::"n"(COUNT) : "memory"); }
+
+template <class T, class Op, bool Inclusive, class S>
+__global__ void __launch_bounds__(S::THREADS)
+scan_kernel(const T* in, T* out, const long long n, const T init, const TileState<T> ts, unsigned* vid_ticket, const int flags,
+            unsigned* trace)
 {
-  constexpr int ITEMS = K * V;
-  constexpr int TILE = BLOCK * ITEMS;
-  constexpr int NW = BLOCK / WARP;
-  constexpr int WARP_ITEMS = WARP * ITEMS;
+  using L = Layout<T, S>;
+  constexpr int BLOCK = S::BLOCK, VPT = S::VPT, SLOTS = S::SLOTS, ROWS = S::ROWS, AHEAD = S::AHEAD;
+  constexpr int V = L::V, ITEMS = L::ITEMS, TILE = L::TILE, NW = L::NW;
   using VT = Vec<T, V>;
 
-  __shared__ long long s_tile;
-  __shared__ T s_warp[NW];
-  __shared__ T s_prefix;
+  extern __shared__ __align__(128) unsigned char smem[];
+  T* const tiles = reinterpret_cast<T*>(smem);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  T* const s_warp = reinterpret_cast<T*>(smem + L::OFF_WARP);      // warp totals of tile i at [(i % 3) * 32 + warp]
+  T* const s_prefix = reinterpret_cast<T*>(smem + L::OFF_PREFIX);  // exclusive prefix of tile i at [i & 1]
+  unsigned* const s_vid = reinterpret_cast<unsigned*>(smem + L::OFF_VID);
 
-  const int tid = threadIdx.x;
-  if (tid == 0) s_tile = (long long)atomicAdd(ticket, 1u);
-  __syncthreads();
-  const long long tile = s_tile;
-  const long long tile_base = tile * TILE;
-  const int w = tid >> 5, l = tid & 31;
-  const long long wbase = tile_base + (long long)w * WARP_ITEMS;
-  const bool full = (tile_base + TILE <= n);
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  const bool is_lb = (w == NW);           // the look-back warp; its lane 0 also owns every bulk copy
+  const bool producer = (tid == BLOCK);   // (bulk groups are per thread)
   Op op;
   const T ident = Op::identity();
+  const T seed = Inclusive ? ident : init;
 
-  // ---- load (in may alias out: coherent loads) --------------------------------
-  T x[K][V];
-  if (full) {
+  if (tid == 0) {
+    *s_vid = atomicAdd(vid_ticket, 1u);
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      VT v = ld_stream_coherent(reinterpret_cast<const VT*>(in + wbase + (long long)(k * WARP + l) * V));
-#pragma unroll
-      for (int j = 0; j < V; ++j) x[k][j] = v.e[j];
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-#pragma unroll
-      for (int j = 0; j < V; ++j) {
-        long long e = wbase + (long long)(k * WARP + l) * V + j;
-        x[k][j] = (e < n) ? ld_stream_coherent(in + e) : ident;
-      }
-    }
+    for (int s = 0; s < SLOTS; ++s) mbar_init(bars + s, 1);
+    fence_mbar_init();
   }
+  __syncthreads();
+  const long long G = gridDim.x;
+  const long long vid = *s_vid;
+  const long long ntiles = (n + TILE - 1) / TILE;
+  const long long my_tiles = vid < ntiles ? (ntiles - vid + G - 1) / G : 0;
+  if (my_tiles == 0) return;
 
-  // ---- thread-local inclusive scan of each row --------------------------------
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-#pragma unroll
-    for (int j = 1; j < V; ++j) x[k][j] = op(x[k][j - 1], x[k][j]);
-  }
+  // Producer: put tile #i of this CTA into its slot.  Full tiles of an aligned input
+  // travel by bulk copy; a ragged or unaligned tile is fetched cooperatively at consume
+  // time, and its mbarrier phase is completed by a plain arrive so every slot sees
+  // exactly one phase per use.
+  auto produce = [&](long long i) {
+    const int s = (int)(i % SLOTS);
+    const long long base = (vid + i * G) * TILE;
+    if ((flags & F_BULK_IN) && base + TILE <= n) {
+      fence_proxy_async();
+      mbar_arrive_expect_tx(bars + s, L::TILE_BYTES);
+      bulk_g2s(tiles + (size_t)s * TILE, in + base, L::TILE_BYTES, bars + s);
+    } else {
+      mbar_arrive(bars + s);
+    }
+  };
 
-  // ---- warp scan across lanes per row, rows chained in registers ---------------
-  T lane_excl[K];  // (+) of everything in this warp before x[k][0]
-  T run = ident;
+  // Compute warps: wait for tile #i, reduce it, leave the warp totals in s_warp, publish
+  // the tile's aggregate.
+  auto reduce_and_publish = [&](long long i) {
+    const int s = (int)(i % SLOTS);
+    const long long tile = vid + i * G;
+    const long long base = tile * TILE;
+    T* const buf = tiles + (size_t)s * TILE;
+    mbar_wait(bars + s, (unsigned)((i / SLOTS) & 1));
+    if (!((flags & F_BULK_IN) && base + TILE <= n)) {
+      const long long rem = n - base;
+      for (int e = tid; e < TILE; e += BLOCK) buf[e] = (e < rem) ? in[base + e] : ident;
+      named_barrier_1<BLOCK>();
+    }
+    T acc = ident;
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    T s = x[k][V - 1];
+    for (int v = 0; v < VPT; ++v) {
+      VT t = reinterpret_cast<const VT*>(buf)[tid * VPT + v];
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc = op(acc, t.e[j]);
+    }
+    // ordered fold across lanes (lower lane on the left)
 #pragma unroll
     for (int d = 1; d < WARP; d <<= 1) {
-      T o = shfl_up(s, d);
-      if (l >= d) s = op(o, s);
+      T o = shfl_up(acc, d);
+      if (l >= d) acc = op(o, acc);
     }
-    T row_total = shfl_idx(s, WARP - 1);
-    T e = shfl_up(s, 1);
-    if (l == 0) e = ident;
-    lane_excl[k] = op(run, e);
-    run = op(run, row_total);
+    T* const wt = s_warp + (i % 3) * 32;
+    if (l == WARP - 1) wt[w] = acc;
+    named_barrier_1<BLOCK>();
+    if (tid == 0) {
+      T a = ident;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) a = op(a, wt[k]);
+      ts.publish(tile, a);
+    }
+  };
+
+  // Look-back warp: exclusive prefix of tile #i = base (+) aggregates of the `dist` tiles
+  // before it, where base is this CTA's own inclusive prefix two rounds back (or the seed).
+  // poll() issues the batch of loads, finish() consumes it (re-polling if a predecessor has
+  // not published yet -- rare, they publish two iterations early).
+  T lb_val[ROWS];
+  bool lb_ok = true;
+  auto poll = [&](long long i) {
+    const long long tile = vid + i * G;
+    const long long span = 2 * G - 1;
+    const long long dist = tile < span ? tile : span;
+    lb_ok = true;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long long d = (long long)r * WARP + l + 1;
+      lb_val[r] = ident;
+      if (d <= dist) lb_ok = ts.peek(tile - d, lb_val[r]) && lb_ok;
+    }
+  };
+  auto finish = [&](long long i, T base_2back) -> T {
+    const long long tile = vid + i * G;
+    if (flags & F_DBG_NO_LOOKBACK) return seed;
+    unsigned polls = 1;
+    while (!__all_sync(FULL_MASK, lb_ok)) {
+      __nanosleep(64);
+      poll(i);
+      ++polls;
+    }
+    // fixed fold order: per lane farthest row first, then lanes farthest (highest) first
+    T c = ident;
+#pragma unroll
+    for (int r = ROWS - 1; r >= 0; --r) c = op(c, lb_val[r]);
+    T rc = shfl_idx(c, WARP - 1 - l);
+    T window = warp_allreduce(rc, op);
+    if (trace && l == 0) trace[tile] = polls;
+    return op((tile >= 2 * G) ? base_2back : seed, window);
+  };
+  auto block_aggregate = [&](long long i) {
+    T a = ident;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) a = op(a, s_warp[(i % 3) * 32 + k]);
+    return a;
+  };
+
+  // ---- prologue: AHEAD tiles in flight, aggregates of tiles 0 and 1, prefix of tile 0 ----
+  T incl_m1 = ident, incl_0 = ident;  // look-back warp: inclusive prefixes of own tiles i-1 and i
+  if (producer) {
+    for (long long i = 0; i < AHEAD && i < my_tiles; ++i) produce(i);
   }
-  if (l == 0) s_warp[w] = run;
+  if (!is_lb) {
+    reduce_and_publish(0);
+    if (my_tiles > 1) reduce_and_publish(1);
+  }
+  __syncthreads();
+  if (is_lb) {
+    poll(0);
+    const T p0 = finish(0, ident);
+    if (l == 0) s_prefix[0] = p0;
+    incl_0 = op(p0, block_aggregate(0));
+  }
   __syncthreads();
 
-  T wprefix = ident, block_agg = ident;
-#pragma unroll
-  for (int i = 0; i < NW; ++i) {
-    T t = s_warp[i];
-    if (i < w) wprefix = op(wprefix, t);
-    block_agg = op(block_agg, t);
-  }
+  for (long long i = 0; i < my_tiles; ++i) {
+    const int s = (int)(i % SLOTS);
+    const long long tile = vid + i * G;
+    const long long base = tile * TILE;
+    const bool full = (base + TILE <= n);
+    const int count = full ? TILE : (int)(n - base);
+    T* const buf = tiles + (size_t)s * TILE;
+    const bool bulk_out = (flags & F_BULK_OUT) && full;
 
-  // ---- decoupled look-back (warp 0) ---------------------------------------------
-  if (w == 0) {
-    T excl = ident;
-    if (tile == 0) {
-      excl = Inclusive ? ident : init;
-      if (l == 0) ts.publish(0, TS_INCLUSIVE, op(excl, block_agg));
-    } else {
-      if (l == 0) ts.publish(tile, TS_AGGREGATE, block_agg);
-      long long pred = tile - 1;
-      while (true) {
-        const long long idx = pred - l;
-        uint32_t st;
-        T val = ident;
-        int spins = 0;
-        do {
-          st = (idx >= 0) ? ts.peek(idx, val) : (uint32_t)TS_INCLUSIVE;
-          if (++spins > 4) __nanosleep(32);
-        } while (__any_sync(FULL_MASK, st == TS_INVALID));
-        if (idx < 0) val = ident;
-        const unsigned incl_mask = __ballot_sync(FULL_MASK, st == TS_INCLUSIVE);
-        const int first = __ffs(incl_mask) - 1;  // nearest predecessor holding an inclusive prefix
-        const bool contrib = (first < 0) || (l <= first);
-        T c = contrib ? val : ident;
-        // fold so that farther tiles stay on the left: reverse lane order
-        T rc = shfl_idx(c, WARP - 1 - l);
-        T window = warp_allreduce(rc, op);
-        excl = op(window, excl);
-        if (first >= 0) break;
-        pred -= WARP;
+    if (is_lb) {
+      if (i + 1 < my_tiles) poll(i + 1);
+      // the slot of tile i-1-LAG is free once its outgoing copy has finished reading it:
+      // refill it with the tile AHEAD of the scan
+      if (producer) {
+        bulk_wait_read<S::LAG>();
+        if (i + AHEAD < my_tiles) produce(i + AHEAD);
       }
-      if (l == 0) ts.publish(tile, TS_INCLUSIVE, op(excl, block_agg));
-    }
-    if (l == 0) s_prefix = excl;
-  }
-  __syncthreads();
-  const T tile_prefix = op(s_prefix, wprefix);
+      if (i + 1 < my_tiles) {
+        const T p = finish(i + 1, incl_m1);
+        if (l == 0) s_prefix[(i + 1) & 1] = p;
+        incl_m1 = incl_0;
+        incl_0 = op(p, block_aggregate(i + 1));
+      }
+    } else {
+      if (i + 2 < my_tiles) reduce_and_publish(i + 2);
 
-  // ---- apply prefix, store ----------------------------------------------------------
+      // ---- scan tile i with its prefix, write it back into the slot ---------------------------
+      T x[ITEMS];
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const T base = op(tile_prefix, lane_excl[k]);
-    VT v;
-    if (Inclusive) {
+      for (int v = 0; v < VPT; ++v) {
+        VT t = reinterpret_cast<const VT*>(buf)[tid * VPT + v];
 #pragma unroll
-      for (int j = 0; j < V; ++j) v.e[j] = op(base, x[k][j]);
-    } else {
-      v.e[0] = base;
+        for (int j = 0; j < V; ++j) x[v * V + j] = t.e[j];
+      }
 #pragma unroll
-      for (int j = 1; j < V; ++j) v.e[j] = op(base, x[k][j - 1]);
+      for (int j = 1; j < ITEMS; ++j) x[j] = op(x[j - 1], x[j]);
+      T sc = x[ITEMS - 1];
+#pragma unroll
+      for (int d = 1; d < WARP; d <<= 1) {
+        T o = shfl_up(sc, d);
+        if (l >= d) sc = op(o, sc);
+      }
+      T lane_excl = shfl_up(sc, 1);
+      if (l == 0) lane_excl = ident;
+      T wprefix = ident;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        T t = s_warp[(i % 3) * 32 + k];
+        if (k < w) wprefix = op(wprefix, t);
+      }
+      const T pre = op(op(s_prefix[i & 1], wprefix), lane_excl);
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        VT t;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const int e = v * V + j;
+          if (Inclusive) t.e[j] = op(pre, x[e]);
+          else t.e[j] = (e == 0) ? pre : op(pre, x[e - 1]);
+        }
+        reinterpret_cast<VT*>(buf)[tid * VPT + v] = t;
+      }
+      if (bulk_out) {
+        fence_proxy_async();  // generic-proxy writes above -> async-proxy read by the bulk store
+      } else {
+        named_barrier_1<BLOCK>();
+        for (int e = tid; e < count; e += BLOCK) out[base + e] = buf[e];
+      }
     }
-    const long long e0 = wbase + (long long)(k * WARP + l) * V;
-    if (full) {
-      st_stream(reinterpret_cast<VT*>(out + e0), v);
-    } else {
-#pragma unroll
-      for (int j = 0; j < V; ++j)
-        if (e0 + j < n) out[e0 + j] = v.e[j];
+    __syncthreads();  // tile i is complete in its slot; prefix(i+1) is in s_prefix
+    if (producer && bulk_out) {
+      bulk_s2g(out + base, buf, L::TILE_BYTES);
+      bulk_commit();
     }
   }
+  if (producer) bulk_wait_all();  // shared memory must outlive the last outgoing copy
 }
 
-// Workspace: [ticket (128 B)] [tile state].  Must be zero before the launch.
-template <class T> inline size_t workspace_bytes(long long ntiles) { return 128 + TileState<T>::bytes(ntiles); }
+// Workspace: [virtual-id ticket (128 B)] [tile state].  Zeroed here, stream-ordered.
+template <class T, class S> inline long long num_tiles(long long n) { return (n + Layout<T, S>::TILE - 1) / Layout<T, S>::TILE; }
+template <class T, class S> inline size_t workspace_bytes(long long n) { return 128 + TileState<T>::bytes(num_tiles<T, S>(n)); }
 
+// Default shapes (tools/tune/tune_scan.cu sweeps them on the GPU box)
 template <class T> struct Tuning {
-  // 4-byte: 384 thr x 20 items = 7680 items (30 KB) per tile; 8-byte: 384 x 12 (36 KB)
-  static constexpr int BLOCK = 384;
-  static constexpr int V = 16 / sizeof(T);
-  static constexpr int K = sizeof(T) == 4 ? 5 : 6;
-  static constexpr int K_UNALIGNED = sizeof(T) == 4 ? 16 : 10;  // V = 1 fallback
+  // 384 compute threads x 7 vectors = 42 KB tiles, 5 slots = 210 KB: one CTA per SM, G = 148,
+  // one look-back batch = 2G-1 = 295 <= 320 aggregates.  Measured 6.17 TB/s (int32) and
+  // 6.32 TB/s (int64) at N = 2^28, 96 % of a device memcpy (profiles/r01_scan_tuning.txt).
+  using shape = Shape<384, 7, 10, 5, 0>;
 };
 
-template <class T> inline long long num_tiles(long long n, bool aligned)
+template <class T, class Op, bool Inclusive, class S>
+inline cudaError_t configure(int* ctas_per_sm)
 {
-  using Tn = Tuning<T>;
-  long long tile = aligned ? (long long)Tn::BLOCK * Tn::K * Tn::V : (long long)Tn::BLOCK * Tn::K_UNALIGNED;
-  return (n + tile - 1) / tile;
+  auto kern = scan_kernel<T, Op, Inclusive, S>;
+  static thread_local int cached = 0;
+  if (cached == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Layout<T, S>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, S::THREADS, Layout<T, S>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    cached = occ > 0 ? occ : 1;
+  }
+  *ctas_per_sm = cached;
+  return cudaSuccess;
 }
 
-template <class T> inline bool vector_aligned(const void* in, const void* out)
-{
-  return (((uintptr_t)in | (uintptr_t)out) & 15u) == 0;
-}
-
-// Enqueue one scan on `stream`.  `workspace` must be workspace_bytes<T>(num_tiles)
-// bytes of device memory; it is zeroed here (stream-ordered).
-template <class T, class Op, bool Inclusive>
-inline cudaError_t launch(cudaStream_t stream, const T* in, T* out, long long n, T init, void* workspace)
+// Enqueue one scan on `stream`.  `workspace` must hold workspace_bytes<T,S>(n) bytes of device memory.
+template <class T, class Op, bool Inclusive, class S = typename Tuning<T>::shape>
+inline cudaError_t launch(cudaStream_t stream, const T* in, T* out, long long n, T init, void* workspace,
+                          int flags_clear = 0, int flags_set = 0, unsigned* trace = nullptr)
 {
   if (n <= 0) return cudaSuccess;
-  using Tn = Tuning<T>;
-  const bool aligned = vector_aligned<T>(in, out);
-  const long long ntiles = num_tiles<T>(n, aligned);
-  cudaError_t e = cudaMemsetAsync(workspace, 0, workspace_bytes<T>(ntiles), stream);
+  int occ = 1;
+  cudaError_t e = configure<T, Op, Inclusive, S>(&occ);
+  if (e != cudaSuccess) return e;
+  const long long ntiles = num_tiles<T, S>(n);
+  e = cudaMemsetAsync(workspace, 0, workspace_bytes<T, S>(n), stream);
   if (e != cudaSuccess) return e;
   TileState<T> ts;
   ts.bind((char*)workspace + 128, ntiles);
-  unsigned* ticket = (unsigned*)workspace;
+  long long grid = (long long)device_info().sm_count * occ;
+  const long long cap = (S::ROWS * WARP + 1) / 2;  // one batch of look-back loads spans two rounds of the grid
+  if (grid > cap) grid = cap;
+  if (grid > ntiles) grid = ntiles;
+  int flags = 0;
+  if (((uintptr_t)in & 15u) == 0) flags |= F_BULK_IN;
+  if (((uintptr_t)out & 15u) == 0) flags |= F_BULK_OUT;
+  flags = (flags & ~flags_clear) | flags_set;
   LaunchScope scope("scan_kernel", stream);
-  if (aligned)
-    scan_kernel<T, Op, Inclusive, Tn::BLOCK, Tn::K, Tn::V><<<(unsigned)ntiles, Tn::BLOCK, 0, stream>>>(in, out, n, init, ts, ticket);
-  else
-    scan_kernel<T, Op, Inclusive, Tn::BLOCK, Tn::K_UNALIGNED, 1><<<(unsigned)ntiles, Tn::BLOCK, 0, stream>>>(in, out, n, init, ts, ticket);
+  scan_kernel<T, Op, Inclusive, S><<<(unsigned)grid, S::THREADS, Layout<T, S>::SMEM_BYTES, stream>>>(in, out, n, init, ts, (unsigned*)workspace, flags,
+                                                                                                      trace);
   return cudaGetLastError();
 }
 

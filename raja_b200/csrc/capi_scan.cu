@@ -9,9 +9,8 @@ namespace {
 
 template <class T, class Op> int scan_t(int inclusive, const T* in, T* out, long long n, const void* init_host, cudaStream_t st)
 {
-  const bool aligned = scan::vector_aligned<T>(in, out);
-  const long long ntiles = scan::num_tiles<T>(n, aligned);
-  Scratch ws(POOL_DEVICE, scan::workspace_bytes<T>(ntiles), st);
+  using Shape = typename scan::Tuning<T>::shape;
+  Scratch ws(POOL_DEVICE, scan::workspace_bytes<T, Shape>(n), st);
   if (!ws.p) return RB200_ENOMEM;
   T init = Op::identity();
   if (!inclusive && init_host) init = *(const T*)init_host;
