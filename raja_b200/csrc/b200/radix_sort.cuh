@@ -221,7 +221,7 @@ template <int MODE> B200_D unsigned match_digit(unsigned d)
 
 // Compile-time shape of the sweep kernel: BLOCK compute threads (+ 64 look-back threads),
 // ITEMS keys per compute thread, MIN_CTAS resident CTAs per SM the register budget is cut for,
-// MATCH 0 = ballot loop / 1 = match.any.
+// MATCH 0 = ballot loop / 1 = match.any / 2 = shared-memory atomicOr masks.
 template <int BLOCK_, int ITEMS_, int MIN_CTAS_, int MATCH_ = 0> struct SweepShape {
   static constexpr int BLOCK = BLOCK_, ITEMS = ITEMS_, MIN_CTAS = MIN_CTAS_, MATCH = MATCH_;
   static constexpr int LB_WARPS = 2;
@@ -231,13 +231,22 @@ template <int BLOCK_, int ITEMS_, int MIN_CTAS_, int MATCH_ = 0> struct SweepSha
   static_assert(TILE < 65536, "tile-local counts must fit the look-back word next to its flags");
 };
 
-template <class U, class VT, class S> struct OnesweepSmem {
+// per (warp, digit): running rank of the digit for this warp, and the peer mask of the row
+// being ranked (MATCH == 2).  8 bytes, read with one LDS.64.
+struct WarpDigit {
+  uint32_t count;
+  uint32_t mask;
+};
+
+template <class U, class VT, class C, class S> struct OnesweepSmem {
   static constexpr int NW = S::BLOCK / WARP;
   static constexpr bool HAS_VALUES = !std::is_same<VT, NoValue>::value;
-  uint32_t whist[NW][RADIX];   // per-warp digit counts -> running rank of (warp, digit)
+  // global positions fit 32 bits whenever the look-back counters do (n < 2^30)
+  using G = typename std::conditional<sizeof(C) == 4, uint32_t, unsigned long long>::type;
+  WarpDigit whist[NW][RADIX];  // per-warp digit counts -> running rank of (warp, digit)
   uint32_t count[RADIX];       // digit counts of this tile
   uint32_t texcl[RADIX];       // first rank of each digit inside this tile
-  long long gbase[RADIX];      // global position of tile-rank r of digit d = gbase[d] + r
+  G gbase[RADIX];              // global position of tile-rank r of digit d = gbase[d] + r (mod 2^bits)
   uint32_t wtot[RADIX / WARP];
   long long tile;
   U keys[S::TILE];
@@ -254,8 +263,9 @@ onesweep_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
                 unsigned* ticket,                                 // zero on entry
                 const int shift, const unsigned dxor)
 {
-  using SM = OnesweepSmem<U, VT, S>;
+  using SM = OnesweepSmem<U, VT, C, S>;
   using F = LookbackFlags<C>;
+  using G = typename SM::G;
   constexpr int BLOCK = S::BLOCK, ITEMS = S::ITEMS, TILE = S::TILE, NW = SM::NW;
   constexpr bool HAS_VALUES = SM::HAS_VALUES;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -264,7 +274,7 @@ onesweep_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
   const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
   const bool compute = tid < BLOCK;
   if (tid == 0) s.tile = (long long)atomicAdd(ticket, 1u);
-  for (int i = tid; i < NW * RADIX; i += S::THREADS) (&s.whist[0][0])[i] = 0;
+  for (int i = tid; i < NW * RADIX * 2; i += S::THREADS) (&s.whist[0][0].count)[i] = 0;
   __syncthreads();
   const long long tile = s.tile;
   const long long tile_base = tile * TILE;
@@ -296,10 +306,14 @@ onesweep_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 
   // ---- phase B: early counts ------------------------------------------------------------------
   if (compute) {
-    uint32_t* const wh = s.whist[w];
+    WarpDigit* const wh = s.whist[w];
+    if (full) {
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      if (full || (wofs + j * WARP + l < tile_count)) atomicAdd(wh + sweep_digit<FLOAT>(key[j], shift, dxor), 1u);
+      for (int j = 0; j < ITEMS; ++j) atomicAdd(&wh[sweep_digit<FLOAT>(key[j], shift, dxor)].count, 1u);
+    } else {
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j)
+        if (wofs + j * WARP + l < tile_count) atomicAdd(&wh[sweep_digit<FLOAT>(key[j], shift, dxor)].count, 1u);
     }
   }
   __syncthreads();
@@ -307,8 +321,8 @@ onesweep_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
     uint32_t cnt = 0;
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
-      const uint32_t t = s.whist[i][tid];
-      s.whist[i][tid] = cnt;
+      const uint32_t t = s.whist[i][tid].count;
+      s.whist[i][tid].count = cnt;
       cnt += t;
     }
     // successors only need this tile's counts: publish them before any ranking work
@@ -329,34 +343,52 @@ onesweep_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
     const uint32_t tile_excl = pre + incl - cnt;
     s.texcl[tid] = tile_excl;
 #pragma unroll
-    for (int i = 0; i < NW; ++i) s.whist[i][tid] += tile_excl;
+    for (int i = 0; i < NW; ++i) s.whist[i][tid].count += tile_excl;
   }
   __syncthreads();
 
   // ---- phase C ----------------------------------------------------------------------------------
   if (compute) {
     // stable ranks + scatter into shared memory in rank order
-    uint32_t* const wh = s.whist[w];
+    WarpDigit* const wh = s.whist[w];
     const unsigned lt = lanemask_lt();
     uint16_t rank[ITEMS];
+    auto rank_and_scatter = [&](auto full_c) {
+      constexpr bool FULL = decltype(full_c)::value;
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-      const bool valid = full || (wofs + j * WARP + l < tile_count);
-      // out-of-range lanes of the ragged tile are masked out of every peer group
-      const unsigned d = sweep_digit<FLOAT>(key[j], shift, dxor);
-      unsigned peers = match_digit<S::MATCH>(d);
-      if (!full) peers &= __ballot_sync(FULL_MASK, valid);
-      const int leader = __ffs(peers) - 1;
-      uint32_t before = 0;
-      if (l == leader && valid) before = atomicAdd(wh + d, (uint32_t)__popc(peers));
-      before = __shfl_sync(FULL_MASK, before, leader);
-      const uint32_t r = before + __popc(peers & lt);
-      rank[j] = (uint16_t)r;
-      if (valid) s.keys[r] = key[j];
-    }
+      for (int j = 0; j < ITEMS; ++j) {
+        const bool valid = FULL || (wofs + j * WARP + l < tile_count);
+        const unsigned d = sweep_digit<FLOAT>(key[j], shift, dxor);
+        uint32_t r;
+        if constexpr (S::MATCH == 2) {
+          // peers through shared memory: every lane ORs its bit into the digit's row mask, reads
+          // (running count, mask) back with one 64-bit load, and the lowest peer advances the
+          // count and clears the mask for the next row
+          if (valid) atomicOr(&wh[d].mask, 1u << l);
+          __syncwarp();
+          const uint2 cm = *reinterpret_cast<const uint2*>(&wh[d]);
+          __syncwarp();
+          if (valid && (cm.y & lt) == 0) *reinterpret_cast<uint2*>(&wh[d]) = make_uint2(cm.x + __popc(cm.y), 0u);
+          __syncwarp();
+          r = cm.x + __popc(cm.y & lt);
+        } else {
+          unsigned peers = match_digit<S::MATCH>(d);
+          if (!FULL) peers &= __ballot_sync(FULL_MASK, valid);
+          const int leader = __ffs(peers) - 1;
+          uint32_t before = 0;
+          if (l == leader && valid) before = atomicAdd(&wh[d].count, (uint32_t)__popc(peers));
+          before = __shfl_sync(FULL_MASK, before, leader);
+          r = before + __popc(peers & lt);
+        }
+        rank[j] = (uint16_t)r;
+        if (valid) s.keys[r] = key[j];
+      }
+    };
+    if (full) rank_and_scatter(std::true_type{});
+    else rank_and_scatter(std::false_type{});
     if constexpr (HAS_VALUES) {
-      VT val[ITEMS];
       if (full) {
+        VT val[ITEMS];
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) val[j] = ld_stream(vals_in + tile_base + wofs + j * WARP + l);
 #pragma unroll
@@ -405,7 +437,7 @@ onesweep_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
         }
         if (all_done) break;
         p -= consumed;
-        if (consumed == 0) __nanosleep(100);
+        if (consumed < B) __nanosleep(consumed == 0 ? 400 : 100);  // do not steal issue slots from the ranking warps
       }
       Quad<C> g;
 #pragma unroll
@@ -413,22 +445,31 @@ onesweep_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
       st_quad(lookback + tile * RADIX + q, g);
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      s.gbase[q + c] = (long long)(bin_base[q + c] + (unsigned long long)prev[c]) - (long long)s.texcl[q + c];
+    for (int c = 0; c < 4; ++c) s.gbase[q + c] = (G)(bin_base[q + c] + (unsigned long long)prev[c]) - (G)s.texcl[q + c];
   }
   __syncthreads();
 
   // ---- phase D: run-coalesced write-out ------------------------------------------------------------
   if (compute) {
-    U* const ko = keys_out;
+    if (full) {
 #pragma unroll
-    for (int m = 0; m < ITEMS; ++m) {
-      const int i = m * BLOCK + tid;
-      if (full || i < tile_count) {
+      for (int m = 0; m < ITEMS; ++m) {
+        const int i = m * BLOCK + tid;
         const U k = s.keys[i];
-        const long long dst = s.gbase[sweep_digit<FLOAT>(k, shift, dxor)] + i;
-        ko[dst] = k;
+        const G dst = s.gbase[sweep_digit<FLOAT>(k, shift, dxor)] + (G)i;
+        keys_out[dst] = k;
         if constexpr (HAS_VALUES) vals_out[dst] = s.vals[i];
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < ITEMS; ++m) {
+        const int i = m * BLOCK + tid;
+        if (i < tile_count) {
+          const U k = s.keys[i];
+          const G dst = s.gbase[sweep_digit<FLOAT>(k, shift, dxor)] + (G)i;
+          keys_out[dst] = k;
+          if constexpr (HAS_VALUES) vals_out[dst] = s.vals[i];
+        }
       }
     }
   }
@@ -439,7 +480,7 @@ onesweep_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 // ---------------------------------------------------------------------------
 template <class U, class VT> struct Tuning {
   static constexpr int ITEMS = sizeof(U) == 4 ? (sizeof(VT) <= 4 ? 24 : 16) : (std::is_same<VT, NoValue>::value ? 16 : 12);
-  using shape = SweepShape<384, ITEMS, 2, 0>;
+  using shape = SweepShape<384, ITEMS, 2, 2>;
 };
 
 template <class U, class VT, class S = typename Tuning<U, VT>::shape> inline long long num_tiles(long long n)
@@ -473,7 +514,7 @@ template <class U, class VT, class C, class S>
 inline cudaError_t launch_pass(cudaStream_t stream, const U* kin, U* kout, const VT* vin, VT* vout, long long n,
                                const unsigned long long* bin_base, void* lookback, unsigned* ticket, int shift, KeyOrder order)
 {
-  using SM = OnesweepSmem<U, VT, S>;
+  using SM = OnesweepSmem<U, VT, C, S>;
   const long long ntiles = num_tiles<U, VT, S>(n);
   const unsigned dxor = digit_xor<U>(order, shift);
   LaunchScope scope("onesweep_kernel", stream);
