@@ -127,6 +127,11 @@ size_t rb200_reduce_multi_loc_offset(rb200_dtype t);
  * in == out selects the in-place variants. */
 int rb200_scan(int inclusive, rb200_op op, rb200_dtype t, const void* in, void* out, int64_t n, const void* init_host,
                rb200_stream_t stream);
+/* Same, seeded with a carry that lives in DEVICE memory (one value of type t; NULL = none):
+ * out[i] = carry (+) [init (+)] x0 (+) ...   The sharded-range policy uses it to continue a scan
+ * across GPUs without a host round trip (carry = fold of the lower ranks' totals). */
+int rb200_scan_carry(int inclusive, rb200_op op, rb200_dtype t, const void* in, void* out, int64_t n, const void* init_host,
+                     const void* carry_dev, rb200_stream_t stream);
 
 /* ---- sorts: policy/cuda/sort.hpp:101-653 ----------------------------------------------- */
 /* Stable; ascending (RAJA::operators::less) unless descending != 0 (operators::greater).

@@ -44,6 +44,7 @@ SIGNATURES = {
     "rb200_reduce_multi_result_bytes": (c_size_t, [c_int]),
     "rb200_reduce_multi_loc_offset": (c_size_t, [c_int]),
     "rb200_scan": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "rb200_scan_carry": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "rb200_sort": (c_int, [c_int, c_void_p, c_int64, c_int, c_void_p]),
     "rb200_sort_pairs": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "rb200_sort_pairs_buffered": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),

@@ -136,8 +136,8 @@ template <int COUNT> B200_D void named_barrier_1() { asm volatile("bar.sync 1, %
 
 template <class T, class Op, bool Inclusive, class S>
 __global__ void __launch_bounds__(S::THREADS)
-scan_kernel(const T* in, T* out, const long long n, const T init, const TileState<T> ts, unsigned* vid_ticket, const int flags,
-            unsigned* trace)
+scan_kernel(const T* in, T* out, const long long n, const T init, const T* carry_dev, const TileState<T> ts, unsigned* vid_ticket,
+            const int flags, unsigned* trace)
 {
   using L = Layout<T, S>;
   constexpr int BLOCK = S::BLOCK, VPT = S::VPT, SLOTS = S::SLOTS, ROWS = S::ROWS, AHEAD = S::AHEAD;
@@ -156,7 +156,10 @@ scan_kernel(const T* in, T* out, const long long n, const T init, const TileStat
   const bool producer = (tid == BLOCK);   // (bulk groups are per thread)
   Op op;
   const T ident = Op::identity();
-  const T seed = Inclusive ? ident : init;
+  // The seed is folded in front of everything: `init` of an exclusive scan, and/or a carry
+  // that lives in device memory (multi-GPU: the fold of the lower ranks' totals).
+  T seed = Inclusive ? ident : init;
+  if (carry_dev) seed = op(*carry_dev, seed);
 
   if (tid == 0) {
     *s_vid = atomicAdd(vid_ticket, 1u);
@@ -395,7 +398,7 @@ inline cudaError_t configure(int* ctas_per_sm)
 // Enqueue one scan on `stream`.  `workspace` must hold workspace_bytes<T,S>(n) bytes of device memory.
 template <class T, class Op, bool Inclusive, class S = typename Tuning<T>::shape>
 inline cudaError_t launch(cudaStream_t stream, const T* in, T* out, long long n, T init, void* workspace,
-                          int flags_clear = 0, int flags_set = 0, unsigned* trace = nullptr)
+                          int flags_clear = 0, int flags_set = 0, unsigned* trace = nullptr, const T* carry_dev = nullptr)
 {
   if (n <= 0) return cudaSuccess;
   int occ = 1;
@@ -415,8 +418,8 @@ inline cudaError_t launch(cudaStream_t stream, const T* in, T* out, long long n,
   if (((uintptr_t)out & 15u) == 0) flags |= F_BULK_OUT;
   flags = (flags & ~flags_clear) | flags_set;
   LaunchScope scope("scan_kernel", stream);
-  scan_kernel<T, Op, Inclusive, S><<<(unsigned)grid, S::THREADS, Layout<T, S>::SMEM_BYTES, stream>>>(in, out, n, init, ts, (unsigned*)workspace, flags,
-                                                                                                      trace);
+  scan_kernel<T, Op, Inclusive, S><<<(unsigned)grid, S::THREADS, Layout<T, S>::SMEM_BYTES, stream>>>(in, out, n, init, carry_dev, ts,
+                                                                                                      (unsigned*)workspace, flags, trace);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,323 @@
+"""Sharded-range execution across the GPUs of one node: one process per GPU, contiguous
+index shards, collectives only where the path has a real exchange step.
+
+    path              local work (b200 kernels)                 exchange (torch.distributed: NCCL on GPUs)
+    forall            on the shard, lambda sees global indices   none
+    reduce sum/min/max  grid reduce -> device scalar             all_reduce (1 element)
+    reduce min/maxloc   grid reduce -> (val, global loc)         all_gather, fold in rank order (first index wins)
+    scan              shard total -> carry -> seeded scan        all_gather of world_size totals
+    sort[_pairs]      local onesweep sort, regular sampling,     all_gather (samples), all_to_all_single (counts),
+                      stable re-sort of the received runs        all_to_all_single (keys, values)
+    atomic histogram  private bins per GPU                       all_reduce over the bins
+
+RAJA has no multi-GPU policy (the reference runs one device per process and leaves the rest
+to MPI); the surface here is the minimal one: a ShardedRange says which contiguous piece of the
+global iteration space this rank owns, and every function takes the LOCAL shard tensors.
+
+The local work goes through an `ops` object.  The default, B200Ops, is the CUDA library and
+nothing else (it raises without a GPU).  tests/ inject a CPU double built on the oracle to
+exercise the exchange logic with the gloo backend.
+"""
+import torch
+import torch.distributed as dist
+
+__all__ = ["ShardedRange", "B200Ops", "reduce_sum", "reduce_min", "reduce_max", "reduce_dot", "reduce_minloc", "reduce_maxloc",
+           "inclusive_scan", "exclusive_scan", "sort", "sort_pairs", "atomic_histogram", "forall_triad", "forall_daxpy"]
+
+
+class ShardedRange:
+    """Rank `rank` of `world` owns global indices [offset, offset + n_local)."""
+
+    def __init__(self, world, rank, n_local=None, offset=None, group=None):
+        self.world, self.rank, self.group = world, rank, group
+        self.n_local = n_local
+        self.offset = offset if offset is not None else (rank * n_local if n_local is not None else None)
+
+    def for_length(self, n_local):
+        """Same range, shard length filled in (equal shards) when it was left open."""
+        if self.n_local == n_local and self.offset is not None:
+            return self
+        return ShardedRange(self.world, self.rank, n_local, self.offset if self.offset is not None else self.rank * n_local, self.group)
+
+    @staticmethod
+    def split(n_global, world, rank, group=None):
+        """Contiguous near-equal shards of a global range (the first n % world ranks get one more)."""
+        base, rem = divmod(n_global, world)
+        n_local = base + (1 if rank < rem else 0)
+        offset = rank * base + min(rank, rem)
+        return ShardedRange(world, rank, n_local, offset, group)
+
+
+class B200Ops:
+    """Local work on the b200 back-end (CUDA tensors; no fallback)."""
+
+    def __init__(self, res=None):
+        from . import api
+        self.api = api
+        self.res = res if res is not None else api.Resource()
+        self.apol = api.b200_exec(async_=True)
+
+    # every method enqueues on self.res.stream and returns device tensors (no host sync)
+    def reduce(self, kind, x):
+        """-> (value tensor [1] of x.dtype, loc tensor [1] int64) on the device"""
+        from ._lib import lib, check
+        val = torch.empty(1, dtype=x.dtype, device=x.device)
+        loc = torch.empty(1, dtype=torch.int64, device=x.device)
+        check(lib.rb200_reduce(kind, self.api._dt(x), x.data_ptr(), x.numel(), val.data_ptr(), loc.data_ptr(), 1, self.res.handle), "reduce")
+        return val, loc
+
+    def dot(self, x, y):
+        from ._lib import lib, check
+        val = torch.empty(1, dtype=x.dtype, device=x.device)
+        check(lib.rb200_reduce_dot(self.api._dt(x), x.data_ptr(), y.data_ptr(), x.numel(), val.data_ptr(), self.res.handle), "dot")
+        return val
+
+    def scan(self, inclusive, op, src, dst, init, carry):
+        from ._lib import lib, check
+        import ctypes
+        import numpy as np
+        dt = self.api._dt(src)
+        init_p = None
+        if init is not None:
+            init_arr = np.array([init], dtype=self.api._NP[dt])
+            init_p = init_arr.ctypes.data_as(ctypes.c_void_p)
+        check(lib.rb200_scan_carry(1 if inclusive else 0, op, dt, src.data_ptr(), dst.data_ptr(), src.numel(), init_p,
+                                   carry.data_ptr() if carry is not None else None, self.res.handle), "scan")
+
+    def sort_pairs(self, keys, vals, descending, keys_alt=None, vals_alt=None):
+        if vals is None:
+            self.api.stable_sort(keys, int(descending), pol=self.apol, res=self.res)
+        else:
+            self.api.stable_sort_pairs(keys, vals, int(descending), pol=self.apol, res=self.res, keys_alt=keys_alt, vals_alt=vals_alt)
+
+    def histogram(self, hist, keys):
+        self.api.atomic_histogram(hist, keys, pol=self.apol, res=self.res)
+
+    def triad(self, a, b, c, s):
+        self.api.forall_triad(a, b, c, s, pol=self.apol, res=self.res)
+
+    def daxpy(self, a, b, s):
+        self.api.forall_daxpy(a, b, s, pol=self.apol, res=self.res)
+
+
+_KIND = {"sum": 0, "min": 1, "max": 2, "minloc": 3, "maxloc": 4}
+_OPS = {0: "plus", 1: "minimum", 2: "maximum"}  # rb200_op values
+
+
+def _ops(ops):
+    return ops if ops is not None else B200Ops()
+
+
+def _identity(op, dtype):
+    if op == 0:
+        return 0
+    info = torch.finfo(dtype) if dtype.is_floating_point else torch.iinfo(dtype)
+    # RAJA::operators::limits: minimum -> max(), maximum -> min() (-FLT_MAX, not -inf)
+    return info.max if op == 1 else info.min
+
+
+def _fold(op, t, dim=0):
+    """fold a small tensor with a rb200_op (plumbing on world_size elements)"""
+    if op == 0:
+        return t.sum(dim=dim, dtype=t.dtype)
+    return t.amin(dim=dim) if op == 1 else t.amax(dim=dim)
+
+
+# ----------------------------------------------------------------------------------------- forall
+def forall_triad(rng, a, b, c, s, ops=None):
+    """elementwise: every rank runs the loop body over its own shard, no exchange"""
+    _ops(ops).triad(a, b, c, s)
+
+
+def forall_daxpy(rng, a, b, s, ops=None):
+    _ops(ops).daxpy(a, b, s)
+
+
+# ----------------------------------------------------------------------------------------- reductions
+def _allreduce(rng, val, red):
+    if rng.world > 1:
+        dist.all_reduce(val, op=red, group=rng.group)
+    return val
+
+
+def reduce_sum(rng, x, ops=None, as_tensor=False):
+    v = _allreduce(rng, _ops(ops).reduce(_KIND["sum"], x)[0], dist.ReduceOp.SUM)
+    return v if as_tensor else v.item()
+
+
+def reduce_min(rng, x, ops=None, as_tensor=False):
+    v = _allreduce(rng, _ops(ops).reduce(_KIND["min"], x)[0], dist.ReduceOp.MIN)
+    return v if as_tensor else v.item()
+
+
+def reduce_max(rng, x, ops=None, as_tensor=False):
+    v = _allreduce(rng, _ops(ops).reduce(_KIND["max"], x)[0], dist.ReduceOp.MAX)
+    return v if as_tensor else v.item()
+
+
+def reduce_dot(rng, x, y, ops=None, as_tensor=False, res=None):
+    v = _allreduce(rng, (_ops(ops) if ops is not None or res is None else B200Ops(res)).dot(x, y), dist.ReduceOp.SUM)
+    return v if as_tensor else v.item()
+
+
+def _reduce_loc(rng, x, kind, ops):
+    rng = rng.for_length(x.numel())
+    val, loc = _ops(ops).reduce(_KIND[kind], x)
+    loc = torch.where(loc >= 0, loc + rng.offset, loc)  # global index; -1 stays "empty shard"
+    if rng.world == 1:
+        return val.item(), int(loc.item())
+    vals = [torch.empty_like(val) for _ in range(rng.world)]
+    locs = [torch.empty_like(loc) for _ in range(rng.world)]
+    dist.all_gather(vals, val, group=rng.group)
+    dist.all_gather(locs, loc, group=rng.group)
+    vals, locs = torch.cat(vals).cpu(), torch.cat(locs).cpu()
+    # fold in rank order; ranks own ascending index ranges, so "strictly better wins" keeps the
+    # FIRST extremum, which is the sequential answer (util/Operators.hpp:555-594)
+    best_v, best_l = None, -1
+    for v, l in zip(vals.tolist(), locs.tolist()):
+        if l < 0:
+            continue
+        if best_l < 0 or (v < best_v if kind == "minloc" else v > best_v):
+            best_v, best_l = v, l
+    if best_l < 0:
+        best_v = vals[0].item()
+    return best_v, best_l
+
+
+def reduce_minloc(rng, x, ops=None):
+    return _reduce_loc(rng, x, "minloc", ops)
+
+
+def reduce_maxloc(rng, x, ops=None):
+    return _reduce_loc(rng, x, "maxloc", ops)
+
+
+# ----------------------------------------------------------------------------------------- scans
+def _scan(rng, inclusive, src, dst, op, init, ops, res):
+    ops = ops if ops is not None else B200Ops(res)
+    carry = None
+    if rng.world > 1:
+        # shard total -> all_gather -> fold of the lower ranks' totals, all on the device
+        total = ops.reduce(op, src)[0]  # rb200_reduce_kind SUM/MIN/MAX == rb200_op PLUS/MINIMUM/MAXIMUM
+        totals = torch.empty(rng.world, dtype=src.dtype, device=src.device)
+        dist.all_gather_into_tensor(totals, total, group=rng.group)
+        lower = totals[:rng.rank]
+        if rng.rank == 0:
+            carry = None
+        else:
+            carry = _fold(op, lower).reshape(1).contiguous()
+    ops.scan(inclusive, op, src, dst, init, carry)
+
+
+def inclusive_scan(rng, src, dst, op=0, ops=None, res=None):
+    _scan(rng, True, src, dst, op, None, ops, res)
+
+
+def exclusive_scan(rng, src, dst, op=0, init=None, ops=None, res=None):
+    _scan(rng, False, src, dst, op, init, ops, res)
+
+
+# ----------------------------------------------------------------------------------------- sorts
+_SIGNED = {torch.uint32: torch.int32, torch.uint64: torch.int64}
+
+
+def _signed_view(t):
+    """same bits as a signed tensor: torch's indexing ops and the collectives do not take uint32/uint64"""
+    return t.view(_SIGNED[t.dtype]) if t.dtype in _SIGNED else t
+
+
+def _wide(small, orig_dtype):
+    """order-preserving int64/float64 copy of a TINY tensor taken from a signed view (samples, probes)"""
+    if orig_dtype == torch.uint32:
+        return small.to(torch.int64) & 0xFFFFFFFF
+    if orig_dtype == torch.uint64:
+        return small ^ torch.iinfo(torch.int64).min
+    if orig_dtype.is_floating_point:
+        return small.to(torch.float64)
+    return small.to(torch.int64)
+
+
+def _bounds(kview, orig_dtype, n, targets, descending):
+    """For each target: how many keys of the locally sorted shard sort strictly before it
+    (ascending: key < t; descending: key >= t ... i.e. the first index whose key sorts at/after t
+    for ascending, after t for descending).  Vectorised binary search, log2(n) tiny gathers."""
+    m = targets.numel()
+    if n == 0:
+        return torch.zeros(m, dtype=torch.int64, device=targets.device)
+    lo = torch.zeros(m, dtype=torch.int64, device=targets.device)
+    hi = torch.full((m,), n, dtype=torch.int64, device=targets.device)
+    for _ in range(max(n, 1).bit_length() + 1):
+        active = lo < hi
+        mid = (lo + hi) // 2
+        v = _wide(kview[mid.clamp(max=max(n - 1, 0))], orig_dtype)
+        right = (v >= targets) if descending else (v < targets)
+        lo = torch.where(active & right, mid + 1, lo)
+        hi = torch.where(active & ~right, mid, hi)
+    return lo
+
+
+def sort_pairs(rng, keys, vals=None, descending=False, ops=None, res=None, keys_alt=None, vals_alt=None, oversample=32):
+    """Stable sample sort.  keys/vals: this rank's shard (sorted in place locally first).
+    Returns (keys_out, vals_out): this rank's piece of the globally sorted sequence -- rank r holds
+    keys that sort before rank r+1's; piece sizes differ (regular sampling bounds them by ~2n/world)."""
+    ops = ops if ops is not None else B200Ops(res)
+    ops.sort_pairs(keys, vals, descending, keys_alt, vals_alt)
+    if rng.world == 1:
+        return keys, vals
+    W, n = rng.world, keys.numel()
+    dev, kdt = keys.device, keys.dtype
+    kview = _signed_view(keys)
+    # regular sampling of the locally sorted shard
+    s = W * oversample
+    padded = torch.zeros(s, dtype=kview.dtype, device=dev)
+    n_samples = min(s, n)
+    if n_samples > 0:
+        pos = ((torch.arange(n_samples, device=dev, dtype=torch.int64) * 2 + 1) * n) // (2 * n_samples)
+        padded[:n_samples] = kview[pos]
+    counts_s = torch.tensor([n_samples], device=dev, dtype=torch.int64)
+    all_counts = torch.empty(W, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_counts, counts_s, group=rng.group)
+    gathered = torch.empty(W * s, dtype=kview.dtype, device=dev)
+    dist.all_gather_into_tensor(gathered, padded, group=rng.group)
+    valid = (torch.arange(s, device=dev).unsqueeze(0) < all_counts.unsqueeze(1)).reshape(-1)
+    pool = torch.sort(_wide(gathered[valid], kdt), descending=descending, stable=True).values  # <= W*s elements: plumbing
+    m = pool.numel()
+    if m > 0:
+        splitters = pool[(torch.arange(1, W, device=dev, dtype=torch.int64) * m) // W]
+        # a key goes to the rank given by the number of splitters that sort at or before it: equal keys
+        # always meet on one rank, so stability only needs the source-rank order to be kept on arrival
+        bounds = _bounds(kview, kdt, n, splitters, descending)
+    else:
+        bounds = torch.zeros(W - 1, dtype=torch.int64, device=dev)
+    edges = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), bounds, torch.tensor([n], dtype=torch.int64, device=dev)])
+    send_counts = (edges[1:] - edges[:-1]).clamp_(min=0)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=rng.group)
+    send_l, recv_l = send_counts.tolist(), recv_counts.tolist()  # split sizes are host-side arguments of the collective
+    n_out = sum(recv_l)
+    kout = torch.empty(n_out, dtype=kview.dtype, device=dev)
+    dist.all_to_all_single(kout, kview, output_split_sizes=recv_l, input_split_sizes=send_l, group=rng.group)
+    keys_out = kout.view(kdt)
+    vals_out = None
+    if vals is not None:
+        vview = _signed_view(vals)
+        vout = torch.empty(n_out, dtype=vview.dtype, device=dev)
+        dist.all_to_all_single(vout, vview, output_split_sizes=recv_l, input_split_sizes=send_l, group=rng.group)
+        vals_out = vout.view(vals.dtype)
+    # the received runs arrive concatenated in source-rank order: a STABLE local sort merges them
+    # and keeps (source rank, local position) order among equal keys
+    ops.sort_pairs(keys_out, vals_out, descending, None, None)
+    return keys_out, vals_out
+
+
+def sort(rng, keys, descending=False, ops=None, res=None):
+    return sort_pairs(rng, keys, None, descending, ops, res)[0]
+
+
+# ----------------------------------------------------------------------------------------- atomics
+def atomic_histogram(rng, hist, keys, ops=None):
+    """private bins per GPU, summed across GPUs"""
+    _ops(ops).histogram(hist, keys)
+    if rng.world > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=rng.group)
+    return hist
