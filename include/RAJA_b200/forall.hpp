@@ -1,0 +1,101 @@
+// forall_impl for b200_exec: replaces policy/cuda/forall.hpp:565-655 (host launch) and :383-542
+// (the four forallp_cuda_kernel variants) with the persistent engine of b200/forall.cuh.
+// Found by ADL from pattern/forall.hpp:192-195 and CallForall (:662-673).
+#ifndef RAJA_B200_FORALL_HPP
+#define RAJA_B200_FORALL_HPP
+
+namespace RAJA
+{
+namespace policy
+{
+namespace b200
+{
+
+// what param_init / param_resolve receive (the reference hands its cudaInfo: MemUtils_CUDA.hpp:380-394)
+struct LaunchInfo
+{
+  int grid;
+  int block;
+  cudaStream_t stream;
+  RAJA::resources::Cuda res;
+};
+
+namespace detail
+{
+// The engine's per-thread body: the user's loop body, the iterator and the parameter pack travel
+// together by value; each thread works on its own copy (what thread_privatize does in the reference,
+// pattern/detail/privatizer.hpp:45-99), so ValOp accumulators inside the pack are thread-private.
+template<typename LoopBody, typename Iterator, typename ForallParam>
+struct Body
+{
+  LoopBody body;
+  Iterator begin;
+  ForallParam params;
+  template<typename Index>
+  __device__ __forceinline__ void operator()(Index i)
+  {
+    if constexpr (RAJA::expt::type_traits::is_ForallParamPack_empty<ForallParam>::value) body(begin[i]);
+    else RAJA::expt::invoke_body(params, body, begin[i]);
+  }
+};
+
+template<typename ExecPol, typename ForallParam>
+struct Finalize
+{
+  template<typename B>
+  __device__ __forceinline__ void operator()(B& b) const
+  {
+    if constexpr (!RAJA::expt::type_traits::is_ForallParamPack_empty<ForallParam>::value)
+      RAJA::expt::ParamMultiplexer::parampack_combine(ExecPol {}, b.params);
+  }
+};
+}  // namespace detail
+
+template<typename Iterable, typename LoopBody, size_t BLOCK_SIZE, bool Async, typename ForallParam>
+RAJA_INLINE concepts::enable_if_t<resources::EventProxy<resources::Cuda>, RAJA::expt::type_traits::is_ForallParamPack<ForallParam>>
+forall_impl(resources::Cuda res, b200_exec<BLOCK_SIZE, Async> const& pol, Iterable&& iter, LoopBody&& loop_body, ForallParam f_params)
+{
+  using Iterator  = camp::decay<decltype(std::begin(iter))>;
+  using LOOP_BODY = camp::decay<LoopBody>;
+  using IndexType = camp::decay<decltype(std::distance(std::begin(iter), std::end(iter)))>;
+  using EXEC_POL  = b200_exec<BLOCK_SIZE, Async>;
+  using BodyT     = detail::Body<LOOP_BODY, Iterator, camp::decay<ForallParam>>;
+  using FinT      = detail::Finalize<EXEC_POL, camp::decay<ForallParam>>;
+  constexpr int UNROLL = 4;
+  constexpr bool empty = RAJA::expt::type_traits::is_ForallParamPack_empty<ForallParam>::value;
+
+  Iterator begin      = std::begin(iter);
+  Iterator end        = std::end(iter);
+  const IndexType len = std::distance(begin, end);
+
+  // only launch if there is something to iterate over (policy/cuda/forall.hpp:598)
+  if (len > 0)
+  {
+    cudaStream_t stream = res.get_stream();
+    LaunchInfo info {::b200::forall_grid<(int)BLOCK_SIZE, UNROLL, IndexType, BodyT, FinT>(len), (int)BLOCK_SIZE, stream, res};
+    if constexpr (!empty) RAJA::expt::ParamMultiplexer::parampack_init(pol, f_params, info);
+    {
+      // classic reducer objects captured by the body set themselves up for this launch when the body
+      // is copied -- exactly once, inside the scope (RAJA_b200/reduce_classic.hpp); later copies (the
+      // by-value kernel argument) just alias that set-up
+      auto make_body = [&]() {
+        RAJA::b200_detail::LaunchScope scope(info.grid, stream);
+        return BodyT {loop_body, begin, f_params};
+      };
+      BodyT body = make_body();
+      RAJA::b200_detail::check(::b200::launch_forall<(int)BLOCK_SIZE, UNROLL, IndexType>(stream, body, len, FinT {}, info.grid), "forall launch");
+    }
+    if constexpr (!empty) RAJA::expt::ParamMultiplexer::parampack_resolve(pol, f_params, info);
+    if (!Async) res.wait();
+  }
+  return resources::EventProxy<resources::Cuda>(res);
+}
+
+// RAJA::synchronize<b200_synchronize>() (policy/cuda/synchronize.hpp:39-42)
+RAJA_INLINE void synchronize_impl(const b200_synchronize&) { RAJA::b200_detail::check(cudaDeviceSynchronize(), "synchronize"); }
+
+}  // namespace b200
+}  // namespace policy
+}  // namespace RAJA
+
+#endif

@@ -1,0 +1,152 @@
+// Policy tags of the b200 back-end (mirrors policy/cuda/policy.hpp:347-361, 410-445, 1257-1620).
+#ifndef RAJA_B200_POLICY_HPP
+#define RAJA_B200_POLICY_HPP
+
+namespace RAJA
+{
+namespace policy
+{
+namespace b200
+{
+
+// The reference's Policy enum is closed (policy/PolicyBase.hpp:29-39).  Reusing Policy::cuda would make
+// the reference's is_cuda_policy-constrained param_* hooks ambiguous with ours, so the family gets a
+// value of its own; Platform::cuda keeps plugins and get_platform (internal/get_platform.hpp:73-81) honest.
+constexpr ::RAJA::Policy policy_id = static_cast<::RAJA::Policy>(64);
+
+// One mapping: a persistent grid (SMs x resident CTAs) walking BLOCK*UNROLL tiles.  The reference's
+// Direct / StridedLoop / occupancy-calculator variants (policy/cuda/policy.hpp:1257-1322) collapse to it.
+template<size_t BLOCK_SIZE, bool Async = false>
+struct b200_exec
+    : public RAJA::make_policy_pattern_launch_platform_t<policy_id,
+                                                         RAJA::Pattern::forall,
+                                                         (Async ? RAJA::Launch::async : RAJA::Launch::sync),
+                                                         RAJA::Platform::cuda>
+{
+  static_assert(BLOCK_SIZE % 32 == 0 && BLOCK_SIZE >= 32 && BLOCK_SIZE <= 1024, "BLOCK_SIZE must be a multiple of 32, at most 1024");
+  static constexpr size_t block_size = BLOCK_SIZE;
+  static constexpr bool async        = Async;
+};
+
+// classic reducer objects (policy/cuda/policy.hpp:1610-1620).  Deterministic: fixed slot order.
+struct b200_reduce
+    : public RAJA::make_policy_pattern_launch_platform_t<policy_id, RAJA::Pattern::reduce, RAJA::Launch::undefined, RAJA::Platform::cuda>
+{};
+
+// atomics: device code uses hardware atomics, host code falls through to host_policy
+// (policy/cuda/policy.hpp:437-445, policy/cuda/atomic.hpp:690-700)
+template<typename host_policy>
+struct b200_atomic_explicit
+{};
+using b200_atomic = b200_atomic_explicit<RAJA::seq_atomic>;
+
+struct b200_synchronize
+    : public RAJA::make_policy_pattern_launch_t<policy_id, RAJA::Pattern::synchronize, RAJA::Launch::sync>
+{};
+
+}  // namespace b200
+}  // namespace policy
+
+using policy::b200::b200_atomic;
+using policy::b200::b200_atomic_explicit;
+using policy::b200::b200_exec;
+using policy::b200::b200_reduce;
+using policy::b200::b200_synchronize;
+template<size_t BLOCK_SIZE>
+using b200_exec_async = policy::b200::b200_exec<BLOCK_SIZE, true>;
+
+namespace resources
+{
+// primary template: util/resource.hpp:44-48; CUDA specialisations: 72-113
+template<size_t BLOCK_SIZE, bool Async>
+struct get_resource<::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async>>
+{
+  using type = camp::resources::Cuda;
+};
+}  // namespace resources
+
+namespace b200_detail
+{
+inline void check(cudaError_t e, const char* what)
+{
+  if (e != cudaSuccess) throw std::runtime_error(std::string("raja_b200: ") + what + ": " + cudaGetErrorString(e));
+}
+inline void check_rc(int rc, const char* what)
+{
+  if (rc != 0) throw std::runtime_error(std::string("raja_b200: ") + what + ": " + rb200_last_error());
+}
+
+// RAJA operator -> kernel-side operator.  The arithmetic plus/minimum/maximum map onto the b200 ones
+// (same identities: util/Operators.hpp:644-656), which unlocks redux.sync for 32-bit integers; anything
+// else is wrapped as is (needs a static identity()).
+template<class Fn, class T>
+struct WrappedOp
+{
+  using value_type = T;
+  RAJA_HOST_DEVICE static T identity() { return Fn::identity(); }
+  RAJA_HOST_DEVICE T operator()(T a, T b) const { return Fn {}(a, b); }
+};
+template<class Fn, class T, class = void>
+struct kernel_op
+{
+  using type = WrappedOp<Fn, T>;
+};
+template<class T>
+struct kernel_op<RAJA::operators::plus<T, T, T>, T, std::enable_if_t<std::is_arithmetic<T>::value>>
+{
+  using type = ::b200::Plus<T>;
+};
+template<class T>
+struct kernel_op<RAJA::operators::minimum<T, T, T>, T, std::enable_if_t<std::is_arithmetic<T>::value>>
+{
+  using type = ::b200::Minimum<T>;
+};
+template<class T>
+struct kernel_op<RAJA::operators::maximum<T, T, T>, T, std::enable_if_t<std::is_arithmetic<T>::value>>
+{
+  using type = ::b200::Maximum<T>;
+};
+
+// The launch a forall_impl is setting up on this host thread.  Classic reducer objects captured in the
+// loop body read it in their copy constructor (the role of tl_status + setup_reducers in the reference,
+// policy/cuda/MemUtils_CUDA.hpp:192-195, 380-394).
+struct LaunchRecord
+{
+  bool active         = false;
+  int grid            = 0;
+  cudaStream_t stream = 0;
+};
+inline LaunchRecord& tl_launch()
+{
+  static thread_local LaunchRecord r;
+  return r;
+}
+struct LaunchScope
+{
+  LaunchScope(int grid, cudaStream_t s)
+  {
+    LaunchRecord& r = tl_launch();
+    r.active = true;
+    r.grid   = grid;
+    r.stream = s;
+  }
+  ~LaunchScope() { tl_launch().active = false; }
+};
+
+// scratch from the stream-ordered pool, returned on scope exit (safe right after enqueue)
+struct Scratch
+{
+  void* p;
+  cudaStream_t s;
+  Scratch(size_t bytes, cudaStream_t st) : p(rb200_device_malloc(bytes, st)), s(st)
+  {
+    if (!p) throw std::runtime_error(std::string("raja_b200: device pool: ") + rb200_last_error());
+  }
+  ~Scratch() { rb200_device_free(p, s); }
+  Scratch(const Scratch&)            = delete;
+  Scratch& operator=(const Scratch&) = delete;
+};
+}  // namespace b200_detail
+}  // namespace RAJA
+
+#endif

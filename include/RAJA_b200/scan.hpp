@@ -1,0 +1,87 @@
+// RAJA::impl::scan::* for b200_exec: replaces policy/cuda/scan.hpp:52-235 (cub::DeviceScan) with the
+// single-pass TMA-staged scan of b200/scan.cuh.  Must be seen before RAJA/pattern/scan.hpp.
+#ifndef RAJA_B200_SCAN_HPP
+#define RAJA_B200_SCAN_HPP
+
+namespace RAJA
+{
+namespace impl
+{
+namespace scan
+{
+namespace b200_detail
+{
+template<bool Inclusive, size_t BLOCK_SIZE, bool Async, typename InIter, typename OutIter, typename Function, typename T>
+inline resources::EventProxy<resources::Cuda> run(resources::Cuda res, InIter begin, InIter end, OutIter out, Function, T init)
+{
+  using Op = typename ::RAJA::b200_detail::kernel_op<Function, T>::type;
+  static_assert(std::is_same<std::remove_cv_t<std::remove_reference_t<decltype(*out)>>, T>::value, "scan: input and output element types must match");
+  static_assert(sizeof(T) == 4 || sizeof(T) == 8, "b200 scan supports 4- and 8-byte element types");
+  const long long n = (long long)(end - begin);  // 64-bit (the reference truncates to int: policy/cuda/scan.hpp:65)
+  if (n > 0)
+  {
+    cudaStream_t stream = res.get_stream();
+    const T* in_p       = &*begin;  // iterators over contiguous storage (pointers, RAJA::Span)
+    T* out_p            = &*out;
+    using Shape         = typename ::b200::scan::Tuning<T>::shape;
+    ::RAJA::b200_detail::Scratch ws(::b200::scan::workspace_bytes<T, Shape>(n), stream);
+    ::RAJA::b200_detail::check(::b200::scan::launch<T, Op, Inclusive>(stream, in_p, out_p, n, init, ws.p), "scan launch");
+    if (!Async) res.wait();
+  }
+  return resources::EventProxy<resources::Cuda>(res);
+}
+}  // namespace b200_detail
+
+template<size_t BLOCK_SIZE, bool Async, typename InputIter, typename Function>
+inline resources::EventProxy<resources::Cuda> inclusive_inplace(resources::Cuda res,
+                                                                 ::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async> const&,
+                                                                 InputIter begin,
+                                                                 InputIter end,
+                                                                 Function binary_op)
+{
+  using T = std::remove_cv_t<std::remove_reference_t<decltype(*begin)>>;
+  return b200_detail::run<true, BLOCK_SIZE, Async>(res, begin, end, begin, binary_op, T {});
+}
+
+template<size_t BLOCK_SIZE, bool Async, typename InputIter, typename Function, typename T>
+inline resources::EventProxy<resources::Cuda> exclusive_inplace(resources::Cuda res,
+                                                                 ::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async> const&,
+                                                                 InputIter begin,
+                                                                 InputIter end,
+                                                                 Function binary_op,
+                                                                 T init)
+{
+  using V = std::remove_cv_t<std::remove_reference_t<decltype(*begin)>>;
+  return b200_detail::run<false, BLOCK_SIZE, Async>(res, begin, end, begin, binary_op, (V)init);
+}
+
+template<size_t BLOCK_SIZE, bool Async, typename InputIter, typename OutputIter, typename Function>
+inline resources::EventProxy<resources::Cuda> inclusive(resources::Cuda res,
+                                                         ::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async> const&,
+                                                         InputIter begin,
+                                                         InputIter end,
+                                                         OutputIter out,
+                                                         Function binary_op)
+{
+  using T = std::remove_cv_t<std::remove_reference_t<decltype(*begin)>>;
+  return b200_detail::run<true, BLOCK_SIZE, Async>(res, begin, end, out, binary_op, T {});
+}
+
+template<size_t BLOCK_SIZE, bool Async, typename InputIter, typename OutputIter, typename Function, typename T>
+inline resources::EventProxy<resources::Cuda> exclusive(resources::Cuda res,
+                                                         ::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async> const&,
+                                                         InputIter begin,
+                                                         InputIter end,
+                                                         OutputIter out,
+                                                         Function binary_op,
+                                                         T init)
+{
+  using V = std::remove_cv_t<std::remove_reference_t<decltype(*begin)>>;
+  return b200_detail::run<false, BLOCK_SIZE, Async>(res, begin, end, out, binary_op, (V)init);
+}
+
+}  // namespace scan
+}  // namespace impl
+}  // namespace RAJA
+
+#endif
