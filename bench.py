@@ -264,6 +264,9 @@ def run_b200(args):
     if not args.no_e2e:
         e2e = run_e2e(rb, rbm, sharded, n, dev, stream, res, world, barrier, min(K, args.e2e_steps))
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = peaks()
