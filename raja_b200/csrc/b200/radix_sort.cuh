@@ -99,40 +99,70 @@ template <bool FLOAT, class U> B200_D unsigned sweep_digit(U k, int shift, unsig
 // ---------------------------------------------------------------------------
 // 1. histograms of every digit position in one read of the keys
 // ---------------------------------------------------------------------------
-template <class U, int BLOCK, int UNROLL>
-__global__ void __launch_bounds__(BLOCK)
+// Shared-memory layout: every digit counter is replicated COLS times and a lane only ever touches
+// column (lane % COLS), so with COLS = 32 the NPASS atomics of one key row hit 32 distinct banks
+// (the plain [pass][digit] layout costs ~3.5 conflict wavefronts per atomic on random keys, which
+// made this kernel LSU-bound at 2.5 TB/s).  One persistent CTA per SM, 128 KB of counters.
+template <class U> struct HistShape {
+  static constexpr int NPASS = sizeof(U);
+  static constexpr int COLS = sizeof(U) == 4 ? 32 : 16;
+  static constexpr int BLOCK = 1024;
+  static constexpr int VEC = 16 / sizeof(U);  // keys per 128-bit load
+  static constexpr int SMEM = NPASS * RADIX * COLS * 4;
+};
+
+template <class U>
+__global__ void __launch_bounds__(HistShape<U>::BLOCK, 1)
 histogram_kernel(const U* __restrict__ keys, const long long n, unsigned long long* __restrict__ ghist, const KeyOrder order)
 {
-  constexpr int NPASS = sizeof(U);
-  __shared__ uint32_t sh[NPASS][RADIX];
-  for (int i = threadIdx.x; i < NPASS * RADIX; i += BLOCK) (&sh[0][0])[i] = 0;
+  using H = HistShape<U>;
+  constexpr int NPASS = H::NPASS, COLS = H::COLS, BLOCK = H::BLOCK, VEC = H::VEC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* const sh = reinterpret_cast<uint32_t*>(smem_raw);  // [NPASS][RADIX][COLS]
+  for (int i = threadIdx.x; i < NPASS * RADIX * COLS; i += BLOCK) sh[i] = 0;
   __syncthreads();
 
-  constexpr long long TILE = (long long)BLOCK * UNROLL;
-  const long long full_tiles = n / TILE;
-  // a block flushes before any 32-bit shared counter could overflow
-  for (long long t = blockIdx.x; t < full_tiles; t += gridDim.x) {
-    U k[UNROLL];
+  uint32_t* const col = sh + (threadIdx.x & (COLS - 1));
+  auto count = [&](U k) {
+    const U ok = to_ordered(k, order);
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) k[u] = ld_stream(keys + t * TILE + (long long)u * BLOCK + threadIdx.x);
+    for (int p = 0; p < NPASS; ++p) atomicAdd(col + (p * RADIX + (int)((ok >> (p * RADIX_BITS)) & U(RADIX - 1))) * COLS, 1u);
+  };
+  // 128-bit loads over the aligned body; a CTA sees < 2^32 keys, so the 32-bit counters cannot overflow
+  const uintptr_t addr = (uintptr_t)keys;
+  long long head = (long long)(((16 - (addr & 15)) & 15) / sizeof(U));
+  if (head > n) head = n;
+  const long long nvec = (n - head) / VEC;
+  using V = Vec<U, VEC>;
+  const V* const body = reinterpret_cast<const V*>(keys + head);
+  constexpr int UNROLL = 4;
+  long long v = (long long)blockIdx.x * BLOCK * UNROLL + threadIdx.x;
+  const long long stride = (long long)gridDim.x * BLOCK * UNROLL;
+  for (; v + (UNROLL - 1) * BLOCK < nvec; v += stride) {
+    V x[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      U ok = to_ordered(k[u], order);
+    for (int u = 0; u < UNROLL; ++u) x[u] = ld_stream(body + v + u * BLOCK);
 #pragma unroll
-      for (int p = 0; p < NPASS; ++p) atomicAdd(&sh[p][(int)((ok >> (p * RADIX_BITS)) & U(RADIX - 1))], 1u);
-    }
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) count(x[u].e[e]);
   }
-  if (blockIdx.x == (unsigned)(full_tiles % gridDim.x)) {
-    for (long long i = full_tiles * TILE + threadIdx.x; i < n; i += BLOCK) {
-      U ok = to_ordered(keys[i], order);
+  for (int u = 0; u < UNROLL; ++u)
+    if (v + u * BLOCK < nvec) {
+      const V x = ld_stream(body + v + u * BLOCK);
 #pragma unroll
-      for (int p = 0; p < NPASS; ++p) atomicAdd(&sh[p][(int)((ok >> (p * RADIX_BITS)) & U(RADIX - 1))], 1u);
+      for (int e = 0; e < VEC; ++e) count(x.e[e]);
     }
+  if (blockIdx.x == 0) {  // unaligned head and the tail shorter than one vector
+    for (long long i = threadIdx.x; i < head; i += BLOCK) count(keys[i]);
+    for (long long i = head + nvec * VEC + threadIdx.x; i < n; i += BLOCK) count(keys[i]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < NPASS * RADIX; i += BLOCK) {
-    uint32_t c = (&sh[0][0])[i];
-    if (c) atomicAdd(ghist + i, (unsigned long long)c);
+  for (int b = threadIdx.x; b < NPASS * RADIX; b += BLOCK) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) c += sh[b * COLS + ((k + threadIdx.x) & (COLS - 1))];  // rotated: conflict-free
+    if (c) atomicAdd(ghist + b, (unsigned long long)c);
   }
 }
 
@@ -219,13 +249,56 @@ template <int MODE> B200_D unsigned match_digit(unsigned d)
   }
 }
 
+// The same match, written so that ptxas emits R2P (digit bits -> predicates) + per bit one VOTE,
+// one SEL (bit ? 0 : ~0) and one LOP3 (peers & (ballot ^ sel)): 28 instructions per row instead of
+// the ~48 the C++ form above compiles to.
+template <int B> B200_D void match_bit(unsigned d, unsigned& peers)
+{
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 m, t, e;\n\t"
+      "and.b32 t, %1, %2;\n\t"
+      "setp.ne.u32 p, t, 0;\n\t"
+      "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+      "selp.b32 e, 0, 0xffffffff, p;\n\t"
+      "lop3.b32 %0, %0, m, e, 0x60;\n\t"
+      "}"
+      : "+r"(peers)
+      : "r"(d), "n"(1u << B));
+}
+B200_D unsigned match_digit_r2p(unsigned d)
+{
+  unsigned peers = FULL_MASK;
+  match_bit<0>(d, peers);
+  match_bit<1>(d, peers);
+  match_bit<2>(d, peers);
+  match_bit<3>(d, peers);
+  match_bit<4>(d, peers);
+  match_bit<5>(d, peers);
+  match_bit<6>(d, peers);
+  match_bit<7>(d, peers);
+  return peers;
+}
+
+// whole 16-byte units inside [first, last) -> L2
+B200_D void prefetch_l2(const void* first, const void* last)
+{
+  const uintptr_t lo = ((uintptr_t)first + 15u) & ~(uintptr_t)15u;
+  const uintptr_t hi = (uintptr_t)last & ~(uintptr_t)15u;
+  if (hi > lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((unsigned)(hi - lo)) : "memory");
+}
+
 // Compile-time shape of the sweep kernel: BLOCK compute threads (+ 64 look-back threads),
 // ITEMS keys per compute thread, MIN_CTAS resident CTAs per SM the register budget is cut for,
 // MATCH 0 = ballot loop / 1 = match.any / 2 = shared-memory atomicOr masks.
-template <int BLOCK_, int ITEMS_, int MIN_CTAS_, int MATCH_ = 0> struct SweepShape {
+template <int BLOCK_, int ITEMS_, int MIN_CTAS_, int MATCH_ = 0, bool PACK_ = false, int PREFETCH_ = 0, int LB_WARPS_ = 2> struct SweepShape {
   static constexpr int BLOCK = BLOCK_, ITEMS = ITEMS_, MIN_CTAS = MIN_CTAS_, MATCH = MATCH_;
-  static constexpr int LB_WARPS = 2;
+  static constexpr bool PACK = PACK_;
+  // late-count kernel: how many tiles ahead the keys are pulled toward L2 (0 = off); about the number
+  // of CTAs resident on the device (148 SMs x MIN_CTAS), so the prefetch lands one tile-lifetime early
+  static constexpr int PREFETCH_TILES = PREFETCH_;
+  static constexpr int LB_WARPS = LB_WARPS_;  // look-back warps: 2 (4 digits per lane) or 1 (8 digits per lane)
   static constexpr int THREADS = BLOCK + LB_WARPS * WARP;
+  static_assert(LB_WARPS == 1 || LB_WARPS == 2, "");
+  static_assert(LB_WARPS == 2 || MATCH_ >= 3, "the early-count kernel is written for two look-back warps");
   static constexpr int TILE = BLOCK * ITEMS;
   static_assert(BLOCK % WARP == 0 && BLOCK >= RADIX, "one digit-owner thread per digit");
   static_assert(TILE < 65536, "tile-local counts must fit the look-back word next to its flags");
@@ -476,6 +549,287 @@ onesweep_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 }
 
 // ---------------------------------------------------------------------------
+// 3b. one onesweep pass, "late counts" (S::MATCH == 3) -- the production kernel
+//
+// The early-counts kernel above touches shared memory ~9 times per key, 2 of them atomics, and ncu
+// shows it LSU-bound (l1tex data-pipe wavefronts 86 % of peak, profiles/r01_onesweep_v3_*).  Here:
+//   * every warp ranks its keys FIRST against warp-private running counters with no atomics at
+//     all: peers by an 8-ballot match (R2P + VOTE/SEL/LOP3 per bit), one broadcast LDS of the
+//     (warp, digit) counter, one STS by the lowest peer;
+//   * the tile's digit counts are then read off the counters' final values by 256 digit-owner
+//     threads (conflict-free sweep), published for the successors, and the counters are turned
+//     into first tile ranks; 32-bit counter stride, so every bank is used;
+//   * per key that leaves LDS + STS (rank), LDS (base) and the scatter: 22 shared-memory
+//     wavefronts per 32 keys instead of 37;
+//   * the keys of the tile PREFETCH_TILES ahead (about one tile-lifetime) and this tile's values
+//     are pulled toward L2 by bulk prefetches issued from the otherwise idle look-back warps;
+//   * the look-back warps run the batched decoupled look-back next to the scatter.
+// PACK (u32 keys + 4-byte values): key and value cross shared memory as ONE 8-byte word.
+// (A persistent, warp-specialised variant with the next tile's keys loaded during the write-out
+//  was tried; ptxas 12.9 spills the key/rank registers in every loop form tried, which costs more
+//  LSU wavefronts than the variant saves -- see DESIGN.md.)
+// ---------------------------------------------------------------------------
+template <class U, class VT, class C, class S> struct LateSmem {
+  static constexpr int NW = S::BLOCK / WARP;
+  static constexpr bool HAS_VALUES = !std::is_same<VT, NoValue>::value;
+  static constexpr bool PACK = S::PACK && HAS_VALUES && sizeof(U) == 4 && sizeof(VT) == 4;
+  using G = typename std::conditional<sizeof(C) == 4, uint32_t, unsigned long long>::type;
+  uint32_t cnt[NW][RADIX];  // running rank of (warp, digit) -> total -> first tile rank
+  uint16_t count[RADIX];    // digit counts of this tile (TILE < 65536)
+  uint32_t texcl[RADIX];    // first rank of each digit inside this tile
+  G gbase[RADIX];           // global position of tile-rank r of digit d = gbase[d] + r (mod 2^bits)
+  uint32_t wtot[RADIX / WARP];
+  long long tile;
+  alignas(16) U keys[S::TILE];
+  typename std::conditional<HAS_VALUES, VT, char>::type vals[HAS_VALUES ? S::TILE : 1];  // PACK: keys..vals is one uint2[TILE]
+};
+
+template <class U, class VT, bool FLOAT, class C, class S>
+__global__ void __launch_bounds__(S::THREADS, S::MIN_CTAS)
+onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
+                     const VT* __restrict__ vals_in, VT* __restrict__ vals_out,
+                     const long long n,
+                     const unsigned long long* __restrict__ bin_base,  // [256] of this pass
+                     C* lookback,                                      // [ntiles][256], zero on entry
+                     unsigned* ticket,                                 // zero on entry
+                     const int shift, const unsigned dxor)
+{
+  using SM = LateSmem<U, VT, C, S>;
+  using F = LookbackFlags<C>;
+  using G = typename SM::G;
+  constexpr int BLOCK = S::BLOCK, ITEMS = S::ITEMS, TILE = S::TILE, NW = SM::NW, LBT = S::LB_WARPS * WARP;
+  constexpr bool HAS_VALUES = SM::HAS_VALUES, PACK = SM::PACK;
+  static_assert(ITEMS % 2 == 0, "ranks are kept two per register");
+  static_assert(S::MATCH == 3, "late-count kernel: ballot match");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SM& s = *reinterpret_cast<SM*>(smem_raw);
+
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  const bool compute = tid < BLOCK;
+  if (tid == 0) s.tile = (long long)atomicAdd(ticket, 1u);
+  for (int i = tid; i < NW * RADIX; i += S::THREADS) (&s.cnt[0][0])[i] = 0;
+  __syncthreads();
+  const long long tile = s.tile;
+  const long long tile_base = tile * TILE;
+  const int tile_count = (int)((n - tile_base) < (long long)TILE ? (n - tile_base) : (long long)TILE);
+  const bool full = (tile_count == TILE);
+  const int wofs = w * (WARP * ITEMS);  // this warp's first item within the tile
+
+  U key[ITEMS];            // warp-striped: item (j, l) is tile item wofs + j*32 + l
+  uint32_t rp[ITEMS / 2];  // two 16-bit ranks per register: warp-local first, tile ranks later
+
+  // ---- phase A + R: keys -> registers, warp-local stable ranks | look-back warps: prefetches -----
+  if (compute) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) key[j] = ld_stream(keys_in + tile_base + wofs + j * WARP + l);
+    } else {
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) {
+        const int i = wofs + j * WARP + l;
+        key[j] = (i < tile_count) ? ld_stream(keys_in + tile_base + i) : U(0);
+      }
+    }
+  } else if (tid == BLOCK) {
+    if constexpr (HAS_VALUES) prefetch_l2(vals_in + tile_base, vals_in + tile_base + tile_count);
+  } else if (tid == BLOCK + 1) {
+    if constexpr (S::PREFETCH_TILES > 0) {  // keys of the tile some CTA claims about one tile-lifetime from now
+      const long long fb = tile_base + (long long)S::PREFETCH_TILES * TILE;
+      if (fb < n) prefetch_l2(keys_in + fb, keys_in + ((n - fb) < (long long)TILE ? n : fb + TILE));
+    }
+  }
+  if (compute) {
+    uint32_t* const wc = s.cnt[w];
+    const unsigned lt = lanemask_lt();
+    auto rank_rows = [&](auto full_c) {
+      constexpr bool FULL = decltype(full_c)::value;
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) {
+        const bool valid = FULL || (wofs + j * WARP + l < tile_count);
+        const unsigned d = sweep_digit<FLOAT>(key[j], shift, dxor);
+        unsigned peers = match_digit_r2p(d);
+        if (!FULL) peers &= __ballot_sync(FULL_MASK, valid);
+        const uint32_t c = wc[d];  // all peers read the same word: broadcast
+        const unsigned below = peers & lt;
+        const uint32_t r = c + __popc(below);
+        __syncwarp();
+        if (valid && below == 0) wc[d] = c + __popc(peers);
+        __syncwarp();
+        if (j & 1) rp[j >> 1] |= r << 16;
+        else rp[j >> 1] = r;
+      }
+    };
+    if (full) rank_rows(std::true_type{});
+    else rank_rows(std::false_type{});
+  }
+  __syncthreads();
+
+  // ---- phase S: digit owners: counts of the tile, published; counters -> first tile ranks ---------
+  if (tid < RADIX) {
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) cnt += s.cnt[i][tid];
+    st_lookback(lookback + tile * RADIX + tid, (C)cnt | (tile == 0 ? F::GLOBAL : F::LOCAL));
+    s.count[tid] = (uint16_t)cnt;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int k = 1; k < WARP; k <<= 1) {
+      const uint32_t o = __shfl_up_sync(FULL_MASK, incl, k);
+      if (l >= k) incl += o;
+    }
+    if (l == 31) s.wtot[w] = incl;
+    asm volatile("bar.sync 1, %0;" ::"n"(RADIX) : "memory");
+    uint32_t pre = 0;
+#pragma unroll
+    for (int i = 0; i < RADIX / WARP; ++i)
+      if (i < w) pre += s.wtot[i];
+    uint32_t run = pre + incl - cnt;
+    s.texcl[tid] = run;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {  // re-read rather than hold NW counts across the scan (register budget)
+      const uint32_t c = s.cnt[i][tid];
+      s.cnt[i][tid] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase C: scatter into shared memory in tile-rank order | look-back -----------------------
+  if (compute) {
+    const uint32_t* const wc = s.cnt[w];
+    uint2* const pairs = reinterpret_cast<uint2*>(s.keys);
+    (void)pairs;
+    auto scatter = [&](auto full_c) {
+      constexpr bool FULL = decltype(full_c)::value;
+      VT val[PACK ? ITEMS : 1];
+      (void)val;
+      if constexpr (PACK) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+          const int i = wofs + j * WARP + l;
+          val[j] = (FULL || i < tile_count) ? ld_stream(vals_in + tile_base + i) : VT(0);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) {
+        const bool valid = FULL || (wofs + j * WARP + l < tile_count);
+        const unsigned d = sweep_digit<FLOAT>(key[j], shift, dxor);
+        const uint32_t r = wc[d] + ((j & 1) ? (rp[j >> 1] >> 16) : (rp[j >> 1] & 0xffffu));
+        if constexpr (PACK) {
+          if (valid) pairs[r] = make_uint2((uint32_t)key[j], bit_cast_<uint32_t>(val[j]));
+        } else {
+          if (valid) s.keys[r] = key[j];
+          if (j & 1) rp[j >> 1] = (rp[j >> 1] & 0xffffu) | (r << 16);
+          else rp[j >> 1] = (rp[j >> 1] & 0xffff0000u) | r;
+        }
+      }
+    };
+    if (full) scatter(std::true_type{});
+    else scatter(std::false_type{});
+    if constexpr (HAS_VALUES && !PACK) {
+      if (full) {
+        VT v[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) v[j] = ld_stream(vals_in + tile_base + wofs + j * WARP + l);
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) s.vals[(j & 1) ? (rp[j >> 1] >> 16) : (rp[j >> 1] & 0xffffu)] = v[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+          const int i = wofs + j * WARP + l;
+          if (i < tile_count) s.vals[(j & 1) ? (rp[j >> 1] >> 16) : (rp[j >> 1] & 0xffffu)] = ld_stream(vals_in + tile_base + i);
+        }
+      }
+    }
+  } else {
+    // look-back warps: lane owns D consecutive digits; batched decoupled look-back, one 128-bit
+    // load = 4 digits of one predecessor tile, B predecessors in flight per lane
+    constexpr int NQ = RADIX / (LBT * 4);  // quads per lane: 1 (two look-back warps) or 2 (one)
+    constexpr int D = 4 * NQ;
+    const int q = (tid - BLOCK) * D;
+    C prev[D] = {};
+    if (tile != 0) {
+      constexpr int B = (sizeof(C) == 4 ? 8 : 4) / NQ;
+      bool done[D] = {};
+      long long p = tile - 1;
+      while (true) {
+        Quad<C> v[B][NQ];
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+#pragma unroll
+          for (int k = 0; k < NQ; ++k) {
+            if (p - b >= 0) v[b][k] = ld_quad(lookback + (p - b) * RADIX + q + 4 * k);
+            else v[b][k] = Quad<C>{{F::GLOBAL, F::GLOBAL, F::GLOBAL, F::GLOBAL}};  // before the first tile: zero, final
+          }
+        int consumed = 0;
+        bool all_done = false;
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          if (all_done) break;
+          bool ok = true;
+#pragma unroll
+          for (int c = 0; c < D; ++c) ok = ok && (done[c] || (v[b][c >> 2].v[c & 3] & ~F::MASK) != 0);
+          if (!__all_sync(FULL_MASK, ok)) break;  // a predecessor has not published yet: re-poll from here
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            if (!done[c]) {
+              prev[c] += v[b][c >> 2].v[c & 3] & F::MASK;
+              if (v[b][c >> 2].v[c & 3] & F::GLOBAL) done[c] = true;
+            }
+          }
+          ++consumed;
+          bool mine = true;
+#pragma unroll
+          for (int c = 0; c < D; ++c) mine = mine && done[c];
+          all_done = __all_sync(FULL_MASK, mine);
+        }
+        if (all_done) break;
+        p -= consumed;
+        if (consumed < B) __nanosleep(consumed == 0 ? 400 : 100);  // leave the issue slots to the scatter
+      }
+#pragma unroll
+      for (int k = 0; k < NQ; ++k) {
+        Quad<C> g;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) g.v[c] = (C)(prev[4 * k + c] + s.count[q + 4 * k + c]) | F::GLOBAL;
+        st_quad(lookback + tile * RADIX + q + 4 * k, g);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) s.gbase[q + c] = (G)(bin_base[q + c] + (unsigned long long)prev[c]) - (G)s.texcl[q + c];
+  }
+  __syncthreads();
+
+  // ---- phase D: run-coalesced write-out ------------------------------------------------------------
+  if (compute) {
+    const uint2* const pairs = reinterpret_cast<const uint2*>(s.keys);
+    (void)pairs;
+    auto write_out = [&](auto full_c) {
+      constexpr bool FULL = decltype(full_c)::value;
+#pragma unroll
+      for (int m = 0; m < ITEMS; ++m) {
+        const int i = m * BLOCK + tid;
+        if (FULL || i < tile_count) {
+          if constexpr (PACK) {
+            const uint2 kv = pairs[i];
+            const G dst = s.gbase[sweep_digit<FLOAT>((U)kv.x, shift, dxor)] + (G)i;
+            keys_out[dst] = (U)kv.x;
+            vals_out[dst] = bit_cast_<VT>(kv.y);
+          } else {
+            const U k = s.keys[i];
+            const G dst = s.gbase[sweep_digit<FLOAT>(k, shift, dxor)] + (G)i;
+            keys_out[dst] = k;
+            if constexpr (HAS_VALUES) vals_out[dst] = s.vals[i];
+          }
+        }
+      }
+    };
+    if (full) write_out(std::true_type{});
+    else write_out(std::false_type{});
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------
 template <class U, class VT> struct Tuning {
@@ -510,24 +864,37 @@ template <auto Kern> inline cudaError_t configure_once(int smem_bytes)
   return cudaSuccess;
 }
 
+template <class U, class VT, bool FLOAT, class C, class S> struct SweepKernel {
+  // MATCH < 3: early-counts kernel; MATCH >= 3: late-counts kernel
+  using SM = typename std::conditional<(S::MATCH >= 3), LateSmem<U, VT, C, S>, OnesweepSmem<U, VT, C, S>>::type;
+  static constexpr auto kernel()
+  {
+    if constexpr (S::MATCH >= 3) return &onesweep_late_kernel<U, VT, FLOAT, C, S>;
+    else return &onesweep_kernel<U, VT, FLOAT, C, S>;
+  }
+};
+
+template <class U, class VT, bool FLOAT, class C, class S>
+inline cudaError_t launch_pass_k(cudaStream_t stream, const U* kin, U* kout, const VT* vin, VT* vout, long long n,
+                                 const unsigned long long* bin_base, void* lookback, unsigned* ticket, int shift, unsigned dxor, long long ntiles)
+{
+  using K = SweepKernel<U, VT, FLOAT, C, S>;
+  constexpr auto kern = K::kernel();
+  cudaError_t e = configure_once<kern>((int)sizeof(typename K::SM));
+  if (e != cudaSuccess) return e;
+  kern<<<(unsigned)ntiles, S::THREADS, sizeof(typename K::SM), stream>>>(kin, kout, vin, vout, n, bin_base, (C*)lookback, ticket, shift, dxor);
+  return cudaGetLastError();
+}
+
 template <class U, class VT, class C, class S>
 inline cudaError_t launch_pass(cudaStream_t stream, const U* kin, U* kout, const VT* vin, VT* vout, long long n,
                                const unsigned long long* bin_base, void* lookback, unsigned* ticket, int shift, KeyOrder order)
 {
-  using SM = OnesweepSmem<U, VT, C, S>;
   const long long ntiles = num_tiles<U, VT, S>(n);
   const unsigned dxor = digit_xor<U>(order, shift);
   LaunchScope scope("onesweep_kernel", stream);
-  if (order.kind == KEY_FLOAT) {
-    cudaError_t e = configure_once<onesweep_kernel<U, VT, true, C, S>>((int)sizeof(SM));
-    if (e != cudaSuccess) return e;
-    onesweep_kernel<U, VT, true, C, S><<<(unsigned)ntiles, S::THREADS, sizeof(SM), stream>>>(kin, kout, vin, vout, n, bin_base, (C*)lookback, ticket, shift, dxor);
-  } else {
-    cudaError_t e = configure_once<onesweep_kernel<U, VT, false, C, S>>((int)sizeof(SM));
-    if (e != cudaSuccess) return e;
-    onesweep_kernel<U, VT, false, C, S><<<(unsigned)ntiles, S::THREADS, sizeof(SM), stream>>>(kin, kout, vin, vout, n, bin_base, (C*)lookback, ticket, shift, dxor);
-  }
-  return cudaGetLastError();
+  if (order.kind == KEY_FLOAT) return launch_pass_k<U, VT, true, C, S>(stream, kin, kout, vin, vout, n, bin_base, lookback, ticket, shift, dxor, ntiles);
+  return launch_pass_k<U, VT, false, C, S>(stream, kin, kout, vin, vout, n, bin_base, lookback, ticket, shift, dxor, ntiles);
 }
 
 // Sorts n keys (and values) held in (keys, vals) using (keys_alt, vals_alt) as the
@@ -549,13 +916,14 @@ inline cudaError_t sort(cudaStream_t stream, U* keys, U* keys_alt, VT* vals, VT*
   cudaError_t e = cudaMemsetAsync(workspace, 0, header + lb_bytes, stream);
   if (e != cudaSuccess) return e;
   {
-    constexpr int HB = 512, HU = 8;
-    long long tiles = (n + HB * HU - 1) / (HB * HU);
-    long long grid = (long long)device_info().sm_count * 4;
-    if (grid > tiles) grid = tiles;
+    using H = HistShape<U>;
+    e = configure_once<histogram_kernel<U>>(H::SMEM);
+    if (e != cudaSuccess) return e;
+    long long grid = (n + H::BLOCK * H::VEC - 1) / (H::BLOCK * H::VEC);
+    if (grid > device_info().sm_count) grid = device_info().sm_count;
     {
       LaunchScope scope("histogram_kernel", stream);
-      histogram_kernel<U, HB, HU><<<(unsigned)grid, HB, 0, stream>>>(keys, n, ghist, order);
+      histogram_kernel<U><<<(unsigned)grid, H::BLOCK, H::SMEM, stream>>>(keys, n, ghist, order);
     }
     {
       LaunchScope scope("scan_bins_kernel", stream);

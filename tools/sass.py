@@ -12,7 +12,7 @@ for f in funcs[1:]:
     dem = subprocess.run(['c++filt', name], capture_output=True, text=True).stdout.strip()
     if re.search(pat, dem):
         print('==', dem[:200])
-        ops = [m.group(1) for m in re.finditer(r'/\*[0-9a-f]{4}\*/\s+(.*?);', f)]
+        ops = [m.group(1) for m in re.finditer(r'/\*[0-9a-f]{4,6}\*/\s+(.*?);', f)]
         print(len(ops), 'instrs')
         for o in [o for o in ops if re.search(filt, o)][:maxlines]:
             print('   ', o)

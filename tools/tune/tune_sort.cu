@@ -59,10 +59,10 @@ template <class S> void run_shape(const Bufs& b)
   unsigned long long h = 0;
   CK(cudaMemcpy(&h, b.bad, 8, cudaMemcpyDeviceToHost));
   int occ = 0;
-  auto kern = rsort::onesweep_kernel<uint32_t, uint32_t, false, uint32_t, S>;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, S::THREADS, sizeof(rsort::OnesweepSmem<uint32_t, uint32_t, uint32_t, S>));
-  printf("BLOCK=%4d ITEMS=%2d MIN_CTAS=%d MATCH=%d tile=%5d smem=%6.1fKB occ=%d : %8.3f ms  %6.2f Gpairs/s  model68 %7.1f GB/s %s\n", S::BLOCK, S::ITEMS, S::MIN_CTAS,
-         S::MATCH, S::TILE, sizeof(rsort::OnesweepSmem<uint32_t, uint32_t, uint32_t, S>) / 1024.0, occ, ms, b.n / ms / 1e6, 68.0 * b.n / ms / 1e6, h ? "MISMATCH" : "ok");
+  using K = rsort::SweepKernel<uint32_t, uint32_t, false, uint32_t, S>;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, K::kernel(), S::THREADS, sizeof(typename K::SM));
+  printf("BLOCK=%4d ITEMS=%2d MIN_CTAS=%d MATCH=%d PACK=%d tile=%5d smem=%6.1fKB occ=%d : %8.3f ms  %6.2f Gpairs/s  model68 %7.1f GB/s %s\n", S::BLOCK, S::ITEMS, S::MIN_CTAS,
+         S::MATCH, (int)S::PACK + 10 * S::LB_WARPS + 1000 * S::PREFETCH_TILES, S::TILE, sizeof(typename K::SM) / 1024.0, occ, ms, b.n / ms / 1e6, 68.0 * b.n / ms / 1e6, h ? "MISMATCH" : "ok");
   fflush(stdout);
 }
 
@@ -97,16 +97,16 @@ int main(int argc, char** argv)
            68.0 * b.n / best / 1e6);
     cudaFree(tmp);
   }
-  run_shape<rsort::SweepShape<384, 24, 2, 0>>(b);
   run_shape<rsort::SweepShape<384, 24, 2, 2>>(b);
-  run_shape<rsort::SweepShape<384, 20, 2, 2>>(b);
-  run_shape<rsort::SweepShape<384, 16, 2, 2>>(b);
-  run_shape<rsort::SweepShape<256, 24, 3, 2>>(b);
-  run_shape<rsort::SweepShape<256, 30, 3, 2>>(b);
-  run_shape<rsort::SweepShape<256, 20, 4, 2>>(b);
-  run_shape<rsort::SweepShape<512, 16, 2, 2>>(b);
-  run_shape<rsort::SweepShape<512, 20, 2, 2>>(b);
-  run_shape<rsort::SweepShape<640, 16, 1, 2>>(b);
-  run_shape<rsort::SweepShape<960, 20, 1, 2>>(b);
+  run_shape<rsort::SweepShape<256, 30, 3, 3, false, 444>>(b);
+  run_shape<rsort::SweepShape<256, 30, 3, 3, false, 300>>(b);
+  run_shape<rsort::SweepShape<256, 30, 3, 3, false, 600>>(b);
+  run_shape<rsort::SweepShape<256, 30, 3, 3, false, 444, 1>>(b);
+  run_shape<rsort::SweepShape<256, 32, 3, 3, false, 444, 1>>(b);
+  run_shape<rsort::SweepShape<256, 32, 3, 3, true, 444, 1>>(b);
+  run_shape<rsort::SweepShape<256, 30, 3, 3, true, 444, 1>>(b);
+  run_shape<rsort::SweepShape<384, 24, 2, 3, false, 296>>(b);
+  run_shape<rsort::SweepShape<384, 28, 2, 3, false, 296, 1>>(b);
+  run_shape<rsort::SweepShape<512, 20, 2, 3, false, 296, 1>>(b);
   return 0;
 }
