@@ -289,7 +289,11 @@ B200_D void prefetch_l2(const void* first, const void* last)
 // Compile-time shape of the sweep kernel: BLOCK compute threads (+ 64 look-back threads),
 // ITEMS keys per compute thread, MIN_CTAS resident CTAs per SM the register budget is cut for,
 // MATCH 0 = ballot loop / 1 = match.any / 2 = shared-memory atomicOr masks.
-template <int BLOCK_, int ITEMS_, int MIN_CTAS_, int MATCH_ = 0, bool PACK_ = false, int PREFETCH_ = 0, int LB_WARPS_ = 2> struct SweepShape {
+template <int BLOCK_, int ITEMS_, int MIN_CTAS_, int MATCH_ = 0, bool PACK_ = false, int PREFETCH_ = 0, int LB_WARPS_ = 2, int LB_BATCH_ = 8, int LB_SLEEP_ = 400>
+struct SweepShape {
+  // late-count kernel: predecessor tiles in flight per look-back lane (32-bit counters), and the
+  // back-off in ns when the nearest predecessor has not published yet
+  static constexpr int LB_BATCH = LB_BATCH_, LB_SLEEP = LB_SLEEP_;
   static constexpr int BLOCK = BLOCK_, ITEMS = ITEMS_, MIN_CTAS = MIN_CTAS_, MATCH = MATCH_;
   static constexpr bool PACK = PACK_;
   // late-count kernel: how many tiles ahead the keys are pulled toward L2 (0 = off); about the number
@@ -749,7 +753,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
     const int q = (tid - BLOCK) * D;
     C prev[D] = {};
     if (tile != 0) {
-      constexpr int B = (sizeof(C) == 4 ? 8 : 4) / NQ;
+      constexpr int B = (sizeof(C) == 4 ? S::LB_BATCH : S::LB_BATCH / 2) / NQ;
       bool done[D] = {};
       long long p = tile - 1;
       while (true) {
@@ -785,7 +789,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
         }
         if (all_done) break;
         p -= consumed;
-        if (consumed < B) __nanosleep(consumed == 0 ? 400 : 100);  // leave the issue slots to the scatter
+        if (consumed < B) __nanosleep(consumed == 0 ? S::LB_SLEEP : S::LB_SLEEP / 4);  // leave the issue slots to the scatter
       }
 #pragma unroll
       for (int k = 0; k < NQ; ++k) {
@@ -832,9 +836,13 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 // ---------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------
+// Shapes picked on B200 with tools/tune/tune_sort.cu (profiles/r01_onesweep_tuning_v3.txt): 256 compute
+// threads + 2 look-back warps, 3 CTAs per SM, late-count kernel, keys of the tile 300 ahead
+// prefetched to L2; ITEMS is what the 64-register budget of that occupancy holds per key/value width.
 template <class U, class VT> struct Tuning {
-  static constexpr int ITEMS = sizeof(U) == 4 ? (sizeof(VT) <= 4 ? 24 : 16) : (std::is_same<VT, NoValue>::value ? 16 : 12);
-  using shape = SweepShape<384, ITEMS, 2, 2>;
+  static constexpr int VB = std::is_same<VT, NoValue>::value ? 0 : (int)sizeof(VT);
+  static constexpr int ITEMS = sizeof(U) == 4 ? (VB <= 4 ? 30 : 20) : (VB == 0 ? 18 : (VB == 4 ? 16 : 14));
+  using shape = SweepShape<256, ITEMS, 3, 3, false, 300>;
 };
 
 template <class U, class VT, class S = typename Tuning<U, VT>::shape> inline long long num_tiles(long long n)

@@ -203,13 +203,22 @@ scan_kernel(const T* in, T* out, const long long n, const T init, const T* carry
       for (int e = tid; e < TILE; e += BLOCK) buf[e] = (e < rem) ? in[base + e] : ident;
       named_barrier_1<BLOCK>();
     }
-    T acc = ident;
+    // per-vector sums first (independent chains), then an ordered pairwise tree over the VPT sums:
+    // depth (V-1) + ceil(log2 VPT) instead of ITEMS-1 -- a serial fold of 14 doubles is
+    // latency-bound on the FP64 pipe (fp64 scans ran at 66 % of the int64 rate)
+    T pv[VPT];
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
       VT t = reinterpret_cast<const VT*>(buf)[tid * VPT + v];
+      pv[v] = t.e[0];
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc = op(acc, t.e[j]);
+      for (int j = 1; j < V; ++j) pv[v] = op(pv[v], t.e[j]);
     }
+#pragma unroll
+    for (int st = 1; st < VPT; st <<= 1)
+#pragma unroll
+      for (int v = 0; v + st < VPT; v += 2 * st) pv[v] = op(pv[v], pv[v + st]);
+    T acc = pv[0];
     // ordered fold across lanes (lower lane on the left)
 #pragma unroll
     for (int d = 1; d < WARP; d <<= 1) {
@@ -315,16 +324,22 @@ scan_kernel(const T* in, T* out, const long long n, const T init, const T* carry
       if (i + 2 < my_tiles) reduce_and_publish(i + 2);
 
       // ---- scan tile i with its prefix, write it back into the slot ---------------------------
-      T x[ITEMS];
+      // inclusive scan inside each 16-byte vector (independent chains), then a serial scan over the
+      // VPT vector totals only: dependent depth (V-1) + (VPT-1) instead of ITEMS-1
+      T x[ITEMS];   // x[v*V + j]: inclusive scan of vector v up to element j
+      T vpre[VPT];  // vpre[v]: total of the vectors before v (v >= 1)
 #pragma unroll
       for (int v = 0; v < VPT; ++v) {
         VT t = reinterpret_cast<const VT*>(buf)[tid * VPT + v];
+        x[v * V] = t.e[0];
 #pragma unroll
-        for (int j = 0; j < V; ++j) x[v * V + j] = t.e[j];
+        for (int j = 1; j < V; ++j) x[v * V + j] = op(x[v * V + j - 1], t.e[j]);
       }
+      vpre[0] = ident;
+      if (VPT > 1) vpre[1] = x[V - 1];
 #pragma unroll
-      for (int j = 1; j < ITEMS; ++j) x[j] = op(x[j - 1], x[j]);
-      T sc = x[ITEMS - 1];
+      for (int v = 2; v < VPT; ++v) vpre[v] = op(vpre[v - 1], x[(v - 1) * V + V - 1]);
+      T sc = (VPT > 1) ? op(vpre[VPT - 1], x[ITEMS - 1]) : x[ITEMS - 1];
 #pragma unroll
       for (int d = 1; d < WARP; d <<= 1) {
         T o = shfl_up(sc, d);
@@ -341,12 +356,12 @@ scan_kernel(const T* in, T* out, const long long n, const T init, const T* carry
       const T pre = op(op(s_prefix[i & 1], wprefix), lane_excl);
 #pragma unroll
       for (int v = 0; v < VPT; ++v) {
+        const T pre_v = (v == 0) ? pre : op(pre, vpre[v]);  // everything before this vector
         VT t;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-          const int e = v * V + j;
-          if (Inclusive) t.e[j] = op(pre, x[e]);
-          else t.e[j] = (e == 0) ? pre : op(pre, x[e - 1]);
+          if (Inclusive) t.e[j] = op(pre_v, x[v * V + j]);
+          else t.e[j] = (j == 0) ? pre_v : op(pre_v, x[v * V + j - 1]);
         }
         reinterpret_cast<VT*>(buf)[tid * VPT + v] = t;
       }
@@ -376,6 +391,12 @@ template <class T> struct Tuning {
   // one look-back batch = 2G-1 = 295 <= 320 aggregates.  Measured 6.17 TB/s (int32) and
   // 6.32 TB/s (int64) at N = 2^28, 96 % of a device memcpy (profiles/r01_scan_tuning.txt).
   using shape = Shape<384, 7, 10, 5, 0>;
+};
+// Floating-point 8-byte scans are bound by the per-round latency of the dependent FP64 adds (DADD
+// 8.3 cycles against 2-3 for IADD: profiles/r01_scan_fp64_notes.txt), not by bandwidth, so they
+// take the largest tile that still leaves four slots: 54 KB, 5.27 TB/s against 4.49 TB/s.
+template <> struct Tuning<double> {
+  using shape = Shape<384, 9, 10, 4, 0>;
 };
 
 template <class T, class Op, bool Inclusive, class S>
