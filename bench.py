@@ -215,7 +215,11 @@ def run_b200(args):
         sort_sets.append((k, v))
     k_alt = torch.empty(n, dtype=torch.int32, device=dev).view(torch.uint32)
     v_alt = torch.empty(n, dtype=torch.int32, device=dev).view(torch.uint32)
-    sharded = rbm.ShardedRange(world, rank) if world > 1 else None
+    sharded = None
+    if world > 1:
+        # exchanges over NVLink peer memory (rb200_comm_*); receive buffers for 1.25x a shard of keys + values
+        comm = None if args.nccl_exchange else rbm.PeerComm(exchange_bytes=(n + n // 4 + 4096) * 8 + 128)
+        sharded = rbm.ShardedRange(world, rank, comm=comm)
 
     stream = torch.cuda.current_stream()
     res = rb.Resource(stream)
@@ -315,7 +319,8 @@ def run_b200(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32+u32", "data": "synthetic",
         "config": {"workload": f"dot(f64)+inclusive_scan(i32)+sort_pairs(u32,u32), N=2^{args.log2n} elements per path per GPU",
                    "l2": "inputs (1-2 GiB each) larger than the 126 MB L2; every step sorts fresh unsorted buffers",
-                   "sharding": "none" if world == 1 else "contiguous shards; allreduce(dot), carry allgather(scan), sample-sort all-to-all(sort)"},
+                   "sharding": "none" if world == 1 else ("contiguous shards; allreduce(dot), carry allgather(scan), sample-sort all-to-all(sort); exchanges by " +
+                                                           ("NCCL collectives" if args.nccl_exchange else "the NVLink peer-memory communicator (sort: fused partition + all-to-all sweep)"))},
         "paths": paths,
         "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (one radix pass, u32 keys + u32 values)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak if achieved else None,
@@ -415,6 +420,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: exchange with NCCL collectives instead of the peer-memory communicator")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -145,6 +145,44 @@ int rb200_sort_pairs(rb200_dtype key_t, void* keys, void* vals, int val_bytes, i
 int rb200_sort_pairs_buffered(rb200_dtype key_t, void* keys, void* keys_alt, void* vals, void* vals_alt, int val_bytes,
                               int64_t n, int descending, rb200_stream_t stream);
 
+/* Stable multi-way split by nsplit <= 7 splitters (the exchange step of the multi-GPU sample sort,
+ * SURVEY.md section 8e; no counterpart in the reference, which is single-device): element i goes
+ * to bucket b = number of splitters that sort at or before keys_in[i], in the order the sorts
+ * above use (ascending / descending, signed and floating keys by value, -0.0 == +0.0); inside a
+ * bucket the input order is kept.  Buckets are written back to back into keys_out / vals_out
+ * (must not alias the inputs).  `splitters_host`: nsplit HOST values of type key_t, already in
+ * sort order.  `counts_dev`: 8 uint64 in DEVICE memory, receives the bucket sizes (unused ones 0).
+ * val_bytes in {0, 4, 8}. */
+int rb200_partition_pairs(rb200_dtype key_t, const void* keys_in, void* keys_out, const void* vals_in, void* vals_out,
+                          int val_bytes, int64_t n, const void* splitters_host, int nsplit, int descending,
+                          uint64_t* counts_dev, rb200_stream_t stream);
+
+/* ---- peer-memory communicator (multi-GPU sharded range) -----------------
+ * No counterpart in the reference (one device per process, MPI left to the application).  Each rank
+ * owns one "symmetric workspace" in device memory that every process of the node has mapped (CUDA
+ * IPC / fabric handles; the caller does the handle exchange, e.g. torch symmetric memory) and
+ * passes the addresses of all of them, as seen by THIS process, in rank order.  The first
+ * rb200_comm_header_bytes() bytes of each workspace belong to the library; the rest is the
+ * caller's (the receive buffers of rb200_comm_exchange_pairs live there).  Calls are collective:
+ * every rank issues the same sequence on its stream. */
+typedef struct rb200_comm* rb200_comm_t;
+int rb200_comm_create(int rank, int world, void* const* ws_ptrs, size_t ws_bytes, rb200_comm_t* out);
+int rb200_comm_destroy(rb200_comm_t c);
+size_t rb200_comm_header_bytes(void);
+/* dst_dev[r * bytes ...] = rank r's src_dev[0 .. bytes); bytes a multiple of 8, <= 504.  One 1-CTA
+ * kernel per rank: stores into the peers' workspaces over NVLink, then waits for their flags. */
+int rb200_comm_allgather_small(rb200_comm_t c, const void* src_dev, int bytes, void* dst_dev, rb200_stream_t stream);
+int rb200_comm_barrier(rb200_comm_t c, rb200_stream_t stream);
+/* Fused stable partition + all-to-all of the sample sort: like rb200_partition_pairs with
+ * nsplit = world - 1, but bucket d is written straight into rank d's receive buffers (at byte
+ * offsets recv_keys_offset / recv_vals_offset of its workspace, recv_capacity elements each), in
+ * source-rank order and, inside one source, in source order.  Synchronises the stream once (the
+ * count matrix decides the write positions); *n_received = elements now in this rank's buffers.
+ * Returns RB200_ENOMEM on every rank if any rank would overflow its receive buffers. */
+int rb200_comm_exchange_pairs(rb200_comm_t c, rb200_dtype key_t, const void* keys_in, const void* vals_in, int val_bytes,
+                              int64_t n, const void* splitters_host, int nsplit, int descending, size_t recv_keys_offset,
+                              size_t recv_vals_offset, int64_t recv_capacity, int64_t* n_received, rb200_stream_t stream);
+
 /* ---- atomics: policy/cuda/atomic.hpp:665-860 (atomicAdd) ----------------------------------- */
 /* hist[keys[i]] += 1 for i in [0,n)  (exercises/atomic-histogram_solution.cpp:199-202).
  * hist_t in {I32, U32, U64, F32, F64}.  aggregate != 0 uses the warp-aggregated add. */

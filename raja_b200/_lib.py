@@ -48,6 +48,14 @@ SIGNATURES = {
     "rb200_sort": (c_int, [c_int, c_void_p, c_int64, c_int, c_void_p]),
     "rb200_sort_pairs": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "rb200_sort_pairs_buffered": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "rb200_partition_pairs": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "rb200_comm_create": (c_int, [c_int, c_int, ctypes.POINTER(c_void_p), c_size_t, ctypes.POINTER(c_void_p)]),
+    "rb200_comm_destroy": (c_int, [c_void_p]),
+    "rb200_comm_header_bytes": (c_size_t, []),
+    "rb200_comm_allgather_small": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "rb200_comm_barrier": (c_int, [c_void_p, c_void_p]),
+    "rb200_comm_exchange_pairs": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_size_t, c_size_t, c_int64,
+                                          ctypes.POINTER(c_int64), c_void_p]),
     "rb200_atomic_histogram": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "rb200_atomic_pi": (c_int, [c_void_p, c_int64, c_int, c_void_p]),
 }

@@ -29,7 +29,7 @@ __all__ = [
     "forall_triad", "forall_daxpy",
     "reduce_sum", "reduce_min", "reduce_max", "reduce_minloc", "reduce_maxloc", "reduce_dot", "reduce_multi",
     "inclusive_scan", "inclusive_scan_inplace", "exclusive_scan", "exclusive_scan_inplace",
-    "sort", "stable_sort", "sort_pairs", "stable_sort_pairs",
+    "sort", "stable_sort", "sort_pairs", "stable_sort_pairs", "partition_pairs",
     "atomic_histogram", "atomic_pi", "pool_trim", "pool_bytes_cached", "sm_count", "PinnedBuffer",
 ]
 
@@ -299,6 +299,27 @@ def sort_pairs(keys, vals, comp=operators.less, pol=None, res=None, keys_alt=Non
 
 
 # ---------------------------------------------------------------------------- atomics
+def partition_pairs(keys_in, keys_out, vals_in, vals_out, splitters, counts, comp=operators.less, pol=None, res=None):
+    """Stable multi-way split by <= 7 splitters (rb200_partition_pairs; the exchange step of the
+    multi-GPU sample sort).  `splitters`: host sequence / numpy array of keys in sort order;
+    `counts`: int64/uint64 device tensor of >= 8 elements, receives the bucket sizes."""
+    _dev(keys_in, keys_out, counts)
+    vb = 0
+    if vals_in is not None:
+        _dev(vals_in, vals_out)
+        vb = vals_in.element_size()
+    if counts.numel() < 8 or counts.element_size() != 8:
+        raise ValueError("partition_pairs: counts must hold 8 64-bit integers")
+    dt = _dt(keys_in)
+    sp = np.ascontiguousarray(np.asarray(splitters, dtype=_NP[dt]))
+    res = _res(res)
+    check(lib.rb200_partition_pairs(dt, keys_in.data_ptr(), keys_out.data_ptr(), vals_in.data_ptr() if vb else None,
+                                    vals_out.data_ptr() if vb else None, vb, keys_in.numel(),
+                                    sp.ctypes.data_as(ctypes.c_void_p) if sp.size else None, int(sp.size), int(comp),
+                                    counts.data_ptr(), res.handle), "partition_pairs")
+    _finish(pol, res)
+
+
 def atomic_histogram(hist, keys, aggregate=False, pol=None, res=None):
     """forall(i){ RAJA::atomicAdd<b200_atomic>(&hist[keys[i]], 1); }"""
     _dev(hist, keys)

@@ -553,6 +553,47 @@ onesweep_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 }
 
 // ---------------------------------------------------------------------------
+// Digit functors of the late-count kernel (passed by value as a kernel argument).
+//   RadixDigit : the 8-bit digit of one LSD pass (shift / xor precomputed on the host)
+//   SplitDigit : multi-way split by up to 7 splitters (multi-GPU sample sort, raja_b200/multi.py):
+//                digit = number of splitters that sort at or before the key, in the same total
+//                order as the sort (KeyOrder); the splitters live in the constant bank, so the
+//                compares cost no registers.
+// ---------------------------------------------------------------------------
+template <class U, bool FLOAT> struct RadixDigit {
+  static constexpr bool PEER_OUT = false;
+  int shift;
+  unsigned dxor;
+  B200_D unsigned operator()(U k) const { return sweep_digit<FLOAT>(k, shift, dxor); }
+};
+constexpr int MAX_SPLITTERS = 7;
+template <class U> struct SplitDigit {
+  static constexpr bool PEER_OUT = false;
+  U s[MAX_SPLITTERS];  // already mapped with to_ordered(), non-decreasing
+  int nsplit;
+  KeyOrder order;
+  B200_D unsigned operator()(U k) const
+  {
+    const U ok = to_ordered(k, order);
+    unsigned d = 0;
+#pragma unroll
+    for (int i = 0; i < MAX_SPLITTERS; ++i)
+      if (i < nsplit) d += (ok >= s[i]) ? 1u : 0u;
+    return d;
+  }
+};
+
+// SplitDigit whose buckets land in DIFFERENT buffers: bucket d is written to kdst[d] / vdst[d]
+// (peer-mapped memory of GPU d over NVLink), at the positions the pass's bin bases give inside
+// that buffer.  This is the fused "partition + all-to-all" of the multi-GPU sample sort: the
+// write-out of the sweep IS the exchange.
+template <class U, class VT> struct PeerSplitDigit : SplitDigit<U> {
+  static constexpr bool PEER_OUT = true;
+  U* kdst[MAX_SPLITTERS + 1];
+  VT* vdst[MAX_SPLITTERS + 1];
+};
+
+// ---------------------------------------------------------------------------
 // 3b. one onesweep pass, "late counts" (S::MATCH == 3) -- the production kernel
 //
 // The early-counts kernel above touches shared memory ~9 times per key, 2 of them atomics, and ncu
@@ -588,7 +629,7 @@ template <class U, class VT, class C, class S> struct LateSmem {
   typename std::conditional<HAS_VALUES, VT, char>::type vals[HAS_VALUES ? S::TILE : 1];  // PACK: keys..vals is one uint2[TILE]
 };
 
-template <class U, class VT, bool FLOAT, class C, class S>
+template <class U, class VT, class DigitFn, class C, class S>
 __global__ void __launch_bounds__(S::THREADS, S::MIN_CTAS)
 onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
                      const VT* __restrict__ vals_in, VT* __restrict__ vals_out,
@@ -596,7 +637,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
                      const unsigned long long* __restrict__ bin_base,  // [256] of this pass
                      C* lookback,                                      // [ntiles][256], zero on entry
                      unsigned* ticket,                                 // zero on entry
-                     const int shift, const unsigned dxor)
+                     const DigitFn digit)
 {
   using SM = LateSmem<U, VT, C, S>;
   using F = LookbackFlags<C>;
@@ -650,7 +691,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 #pragma unroll
       for (int j = 0; j < ITEMS; ++j) {
         const bool valid = FULL || (wofs + j * WARP + l < tile_count);
-        const unsigned d = sweep_digit<FLOAT>(key[j], shift, dxor);
+        const unsigned d = digit(key[j]);
         unsigned peers = match_digit_r2p(d);
         if (!FULL) peers &= __ballot_sync(FULL_MASK, valid);
         const uint32_t c = wc[d];  // all peers read the same word: broadcast
@@ -717,7 +758,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 #pragma unroll
       for (int j = 0; j < ITEMS; ++j) {
         const bool valid = FULL || (wofs + j * WARP + l < tile_count);
-        const unsigned d = sweep_digit<FLOAT>(key[j], shift, dxor);
+        const unsigned d = digit(key[j]);
         const uint32_t r = wc[d] + ((j & 1) ? (rp[j >> 1] >> 16) : (rp[j >> 1] & 0xffffu));
         if constexpr (PACK) {
           if (valid) pairs[r] = make_uint2((uint32_t)key[j], bit_cast_<uint32_t>(val[j]));
@@ -816,14 +857,26 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
         if (FULL || i < tile_count) {
           if constexpr (PACK) {
             const uint2 kv = pairs[i];
-            const G dst = s.gbase[sweep_digit<FLOAT>((U)kv.x, shift, dxor)] + (G)i;
-            keys_out[dst] = (U)kv.x;
-            vals_out[dst] = bit_cast_<VT>(kv.y);
+            const unsigned d = digit((U)kv.x);
+            const G dst = s.gbase[d] + (G)i;
+            if constexpr (DigitFn::PEER_OUT) {
+              digit.kdst[d][dst] = (U)kv.x;
+              digit.vdst[d][dst] = bit_cast_<VT>(kv.y);
+            } else {
+              keys_out[dst] = (U)kv.x;
+              vals_out[dst] = bit_cast_<VT>(kv.y);
+            }
           } else {
             const U k = s.keys[i];
-            const G dst = s.gbase[sweep_digit<FLOAT>(k, shift, dxor)] + (G)i;
-            keys_out[dst] = k;
-            if constexpr (HAS_VALUES) vals_out[dst] = s.vals[i];
+            const unsigned d = digit(k);
+            const G dst = s.gbase[d] + (G)i;
+            if constexpr (DigitFn::PEER_OUT) {
+              digit.kdst[d][dst] = k;
+              if constexpr (HAS_VALUES) digit.vdst[d][dst] = s.vals[i];
+            } else {
+              keys_out[dst] = k;
+              if constexpr (HAS_VALUES) vals_out[dst] = s.vals[i];
+            }
           }
         }
       }
@@ -877,7 +930,7 @@ template <class U, class VT, bool FLOAT, class C, class S> struct SweepKernel {
   using SM = typename std::conditional<(S::MATCH >= 3), LateSmem<U, VT, C, S>, OnesweepSmem<U, VT, C, S>>::type;
   static constexpr auto kernel()
   {
-    if constexpr (S::MATCH >= 3) return &onesweep_late_kernel<U, VT, FLOAT, C, S>;
+    if constexpr (S::MATCH >= 3) return &onesweep_late_kernel<U, VT, RadixDigit<U, FLOAT>, C, S>;
     else return &onesweep_kernel<U, VT, FLOAT, C, S>;
   }
 };
@@ -890,7 +943,10 @@ inline cudaError_t launch_pass_k(cudaStream_t stream, const U* kin, U* kout, con
   constexpr auto kern = K::kernel();
   cudaError_t e = configure_once<kern>((int)sizeof(typename K::SM));
   if (e != cudaSuccess) return e;
-  kern<<<(unsigned)ntiles, S::THREADS, sizeof(typename K::SM), stream>>>(kin, kout, vin, vout, n, bin_base, (C*)lookback, ticket, shift, dxor);
+  if constexpr (S::MATCH >= 3)
+    kern<<<(unsigned)ntiles, S::THREADS, sizeof(typename K::SM), stream>>>(kin, kout, vin, vout, n, bin_base, (C*)lookback, ticket, RadixDigit<U, FLOAT>{shift, dxor});
+  else
+    kern<<<(unsigned)ntiles, S::THREADS, sizeof(typename K::SM), stream>>>(kin, kout, vin, vout, n, bin_base, (C*)lookback, ticket, shift, dxor);
   return cudaGetLastError();
 }
 
@@ -954,6 +1010,118 @@ inline cudaError_t sort(cudaStream_t stream, U* keys, U* keys_alt, VT* vals, VT*
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------
+// Stable multi-way partition by splitters (one late-count sweep with SplitDigit): element i goes
+// to bucket b = number of splitters that sort at or before keys[i]; inside a bucket the input
+// order is kept.  counts[0 .. nsplit] (device, u64) receives the bucket sizes.  Used by the
+// multi-GPU sample sort: partition -> all-to-all -> ONE local sort (raja_b200/multi.py).
+// ---------------------------------------------------------------------------
+template <class U, class DigitFn, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) bucket_count_kernel(const U* __restrict__ keys, const long long n, unsigned long long* __restrict__ ghist, const DigitFn digit)
+{
+  // per-thread counters for the 8 possible buckets, folded by warp shuffles, one global atomic per warp and bucket
+  unsigned c[MAX_SPLITTERS + 1] = {};
+  for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * BLOCK) {
+    const unsigned d = digit(ld_stream(keys + i));
+#pragma unroll
+    for (int b = 0; b <= MAX_SPLITTERS; ++b) c[b] += (d == (unsigned)b) ? 1u : 0u;
+  }
+#pragma unroll
+  for (int b = 0; b <= MAX_SPLITTERS; ++b) {
+    unsigned v = c[b];
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) v += __shfl_xor_sync(FULL_MASK, v, k);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(ghist + b, (unsigned long long)v);
+  }
+}
+
+template <class U, class VT> struct PartitionTuning {
+  // the splitter digit costs ~16 instructions where the radix digit costs 2: a smaller ITEMS keeps
+  // the three digit evaluations per key inside the register budget
+  static constexpr int VB = std::is_same<VT, NoValue>::value ? 0 : (int)sizeof(VT);
+  static constexpr int ITEMS = sizeof(U) == 4 ? (VB <= 4 ? 24 : 16) : (VB == 0 ? 14 : 12);
+  using shape = SweepShape<256, ITEMS, 3, 3, false, 300>;
+};
+
+// workspace: same layout as sort's ([ghist 256 u64 x NPASS][bin_base ...][tickets][lookback]); only pass 0 is used
+template <class U, class VT, class S = typename PartitionTuning<U, VT>::shape> inline size_t partition_workspace_bytes(long long n)
+{
+  return workspace_bytes<U, VT, S>(n);
+}
+
+// bucket sizes of a split: counts_dev[0 .. MAX_SPLITTERS] (u64, device); workspace as for partition()
+template <class U, class VT, class S = typename PartitionTuning<U, VT>::shape>
+inline cudaError_t bucket_counts(cudaStream_t stream, const U* keys_in, long long n, const SplitDigit<U>& digit, unsigned long long* counts_dev, void* workspace)
+{
+  constexpr int NPASS = sizeof(U);
+  const size_t header = (size_t)NPASS * RADIX * 8 * 2 + 256;
+  unsigned long long* ghist = (unsigned long long*)workspace;
+  const bool small = n < (1ll << 30);
+  const long long ntiles = num_tiles<U, VT, S>(n > 0 ? n : 1);
+  const size_t lb_bytes = (size_t)ntiles * RADIX * (small ? 4 : 8);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, header + lb_bytes, stream);
+  if (e != cudaSuccess) return e;
+  if (n > 0) {
+    constexpr int CB = 512;
+    long long grid = (n + CB * 8 - 1) / (CB * 8);
+    const long long cap = (long long)device_info().sm_count * 4;
+    if (grid > cap) grid = cap;
+    LaunchScope scope("bucket_count_kernel", stream);
+    bucket_count_kernel<U, SplitDigit<U>, CB><<<(unsigned)grid, CB, 0, stream>>>(keys_in, n, ghist, digit);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaMemcpyAsync(counts_dev, ghist, (MAX_SPLITTERS + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream);
+}
+
+// the sweep of a split; bucket_counts() must have run on the same workspace.  bases_host == nullptr:
+// buckets back to back in (keys_out, vals_out) (exclusive scan of the counts on the device);
+// otherwise bucket d starts at element bases_host[d] of ITS destination (PeerSplitDigit).
+template <class U, class VT, class DigitFn, class S = typename PartitionTuning<U, VT>::shape>
+inline cudaError_t split_sweep(cudaStream_t stream, const U* keys_in, U* keys_out, const VT* vals_in, VT* vals_out, long long n, const DigitFn& digit,
+                               const unsigned long long* bases_host, void* workspace)
+{
+  if (n <= 0) return cudaSuccess;
+  constexpr int NPASS = sizeof(U);
+  const size_t header = (size_t)NPASS * RADIX * 8 * 2 + 256;
+  unsigned long long* ghist = (unsigned long long*)workspace;
+  unsigned long long* bin_base = ghist + NPASS * RADIX;
+  unsigned* tickets = (unsigned*)(bin_base + NPASS * RADIX);
+  void* lookback = (char*)workspace + header;
+  const bool small = n < (1ll << 30);
+  const long long ntiles = num_tiles<U, VT, S>(n);
+  cudaError_t e;
+  if (bases_host) {
+    e = cudaMemcpyAsync(bin_base, bases_host, (MAX_SPLITTERS + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+  } else {
+    LaunchScope scope("scan_bins_kernel", stream);
+    scan_bins_kernel<<<1, RADIX, 0, stream>>>(ghist, bin_base);
+  }
+  LaunchScope scope("onesweep_kernel", stream);
+  if (small) {
+    constexpr auto kern = &onesweep_late_kernel<U, VT, DigitFn, uint32_t, S>;
+    e = configure_once<kern>((int)sizeof(LateSmem<U, VT, uint32_t, S>));
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)ntiles, S::THREADS, sizeof(LateSmem<U, VT, uint32_t, S>), stream>>>(keys_in, keys_out, vals_in, vals_out, n, bin_base, (uint32_t*)lookback, tickets, digit);
+  } else {
+    constexpr auto kern = &onesweep_late_kernel<U, VT, DigitFn, unsigned long long, S>;
+    e = configure_once<kern>((int)sizeof(LateSmem<U, VT, unsigned long long, S>));
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)ntiles, S::THREADS, sizeof(LateSmem<U, VT, unsigned long long, S>), stream>>>(keys_in, keys_out, vals_in, vals_out, n, bin_base, (unsigned long long*)lookback, tickets, digit);
+  }
+  return cudaGetLastError();
+}
+
+template <class U, class VT, class S = typename PartitionTuning<U, VT>::shape>
+inline cudaError_t partition(cudaStream_t stream, const U* keys_in, U* keys_out, const VT* vals_in, VT* vals_out, long long n,
+                             const SplitDigit<U>& digit, unsigned long long* counts_dev, void* workspace)
+{
+  cudaError_t e = bucket_counts<U, VT, S>(stream, keys_in, n, digit, counts_dev, workspace);
+  if (e != cudaSuccess) return e;
+  return split_sweep<U, VT, SplitDigit<U>, S>(stream, keys_in, keys_out, vals_in, vals_out, n, digit, nullptr, workspace);
 }
 
 }  // namespace rsort

@@ -6,8 +6,10 @@ index shards, collectives only where the path has a real exchange step (SURVEY.m
     reduce sum/min/max  grid reduce -> device scalar             all_reduce (1 element)
     reduce min/maxloc   grid reduce -> (val, global loc)         all_gather, fold in rank order (first index wins)
     scan              shard total -> carry -> seeded scan        all_gather of world_size totals
-    sort[_pairs]      local onesweep sort, regular sampling,     all_gather (samples), all_to_all_single (counts),
-                      stable re-sort of the received runs        all_to_all_single (keys, values)
+    sort[_pairs]      regular sampling of the UNSORTED shard,    all_gather (samples), all_to_all_single (counts),
+                      one stable splitter partition (a single    all_to_all_single (keys, values)
+                      onesweep pass), ONE local onesweep sort
+                      of what arrives
     atomic histogram  private bins per GPU                       all_reduce over the bins
 
 RAJA has no multi-GPU policy (the reference runs one device per process and leaves the rest
@@ -21,15 +23,16 @@ exercise the exchange logic with the gloo backend.
 import torch
 import torch.distributed as dist
 
-__all__ = ["ShardedRange", "B200Ops", "reduce_sum", "reduce_min", "reduce_max", "reduce_dot", "reduce_minloc", "reduce_maxloc",
+__all__ = ["ShardedRange", "B200Ops", "PeerComm", "reduce_sum", "reduce_min", "reduce_max", "reduce_dot", "reduce_minloc", "reduce_maxloc",
            "inclusive_scan", "exclusive_scan", "sort", "sort_pairs", "atomic_histogram", "forall_triad", "forall_daxpy"]
 
 
 class ShardedRange:
     """Rank `rank` of `world` owns global indices [offset, offset + n_local)."""
 
-    def __init__(self, world, rank, n_local=None, offset=None, group=None):
+    def __init__(self, world, rank, n_local=None, offset=None, group=None, comm=None):
         self.world, self.rank, self.group = world, rank, group
+        self.comm = comm  # PeerComm: exchanges go over NVLink peer memory instead of torch.distributed collectives
         self.n_local = n_local
         self.offset = offset if offset is not None else (rank * n_local if n_local is not None else None)
 
@@ -37,7 +40,7 @@ class ShardedRange:
         """Same range, shard length filled in (equal shards) when it was left open."""
         if self.n_local == n_local and self.offset is not None:
             return self
-        return ShardedRange(self.world, self.rank, n_local, self.offset if self.offset is not None else self.rank * n_local, self.group)
+        return ShardedRange(self.world, self.rank, n_local, self.offset if self.offset is not None else self.rank * n_local, self.group, self.comm)
 
     @staticmethod
     def split(n_global, world, rank, group=None):
@@ -46,6 +49,83 @@ class ShardedRange:
         n_local = base + (1 if rank < rem else 0)
         offset = rank * base + min(rank, rem)
         return ShardedRange(world, rank, n_local, offset, group)
+
+
+class PeerComm:
+    """NVLink / NVSwitch peer-memory communicator (rb200_comm_* in include/raja_b200.h).
+
+    Every rank owns one symmetric workspace that all processes of the node have mapped (torch
+    symmetric memory does the handle exchange: plumbing); the library's kernels store straight into
+    the peers' workspaces.  Used for the small exchanges of the sharded paths (one 1-CTA kernel
+    instead of a NCCL collective) and for the sort, whose splitter sweep writes every bucket directly
+    into its destination GPU (fused partition + all-to-all).  `exchange_bytes`: room for the sort's
+    receive buffers (keys and values of ~1.25x a shard); 0 = small exchanges only."""
+
+    def __init__(self, group=None, exchange_bytes=0, device=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        from ._lib import lib, check
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.header = int(lib.rb200_comm_header_bytes())
+        self.nbytes = self.header + ((int(exchange_bytes) + 63) // 64) * 64
+        self.buf = symm.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
+        handle = ctypes.c_void_p()
+        check(lib.rb200_comm_create(self.rank, self.world, ptrs, self.nbytes, ctypes.byref(handle)), "comm_create")
+        self.handle = handle
+        torch.cuda.synchronize(self.device)
+        self.hdl.barrier()  # every header is zeroed before anyone stores into it
+
+    def close(self):
+        from ._lib import lib
+        if getattr(self, "handle", None):
+            lib.rb200_comm_destroy(self.handle)
+            self.handle = None
+
+    def allgather_small(self, t, res):
+        """t: small contiguous device tensor -> [world, *t.shape] in rank order (stream ordered, no host sync)"""
+        from ._lib import lib, check
+        nb = t.numel() * t.element_size()
+        pad = (-nb) % 8
+        src = t.contiguous().view(torch.uint8).reshape(-1)
+        if pad:
+            src = torch.cat([src, torch.zeros(pad, dtype=torch.uint8, device=t.device)])
+        out = torch.empty(self.world, nb + pad, dtype=torch.uint8, device=t.device)
+        check(lib.rb200_comm_allgather_small(self.handle, src.data_ptr(), nb + pad, out.data_ptr(), res.handle), "comm_allgather_small")
+        return out[:, :nb].contiguous().view(t.dtype).reshape(self.world, *t.shape)
+
+    def barrier(self, res):
+        from ._lib import lib, check
+        check(lib.rb200_comm_barrier(self.handle, res.handle), "comm_barrier")
+
+    def capacity(self, key_bytes, val_bytes):
+        """elements the receive buffers of one exchange can take"""
+        return max((self.nbytes - self.header - 64) // (key_bytes + val_bytes), 0)
+
+    def exchange_pairs(self, keys, vals, splitters, descending, res):
+        """fused partition + all-to-all -> (keys_recv, vals_recv): views of this rank's receive buffers,
+        valid until the next exchange on this communicator"""
+        import ctypes
+        import numpy as np
+        from ._lib import lib, check
+        from . import api
+        ks, vb = keys.element_size(), (vals.element_size() if vals is not None else 0)
+        cap = self.capacity(ks, vb)
+        koff = self.header
+        voff = koff + ((cap * ks + 63) // 64) * 64
+        dt = api._dt(keys)
+        sp = np.ascontiguousarray(np.asarray(splitters, dtype=api._NP[dt]))
+        got = ctypes.c_int64(0)
+        check(lib.rb200_comm_exchange_pairs(self.handle, dt, keys.data_ptr(), vals.data_ptr() if vb else None, vb, keys.numel(),
+                                            sp.ctypes.data_as(ctypes.c_void_p) if sp.size else None, int(sp.size), int(descending),
+                                            koff, voff, cap, ctypes.byref(got), res.handle), "comm_exchange_pairs")
+        n_out = int(got.value)
+        kout = self.buf[koff:koff + n_out * ks].view(keys.dtype)
+        vout = self.buf[voff:voff + n_out * vb].view(vals.dtype) if vb else None
+        return kout, vout
 
 
 class B200Ops:
@@ -89,6 +169,16 @@ class B200Ops:
             self.api.stable_sort(keys, int(descending), pol=self.apol, res=self.res)
         else:
             self.api.stable_sort_pairs(keys, vals, int(descending), pol=self.apol, res=self.res, keys_alt=keys_alt, vals_alt=vals_alt)
+
+    def partition_pairs(self, keys, vals, splitters, descending, keys_out=None, vals_out=None):
+        """stable split of (keys, vals) by the host `splitters` -> (keys_out, vals_out, counts int64[8] on the device)"""
+        keys_out = keys_out if keys_out is not None else torch.empty_like(keys)
+        if vals is not None and vals_out is None:
+            vals_out = torch.empty_like(vals)
+        counts = torch.zeros(8, dtype=torch.int64, device=keys.device)
+        self.api.partition_pairs(keys, keys_out, vals, vals_out if vals is not None else None, splitters, counts, int(descending),
+                                 pol=self.apol, res=self.res)
+        return keys_out, (vals_out if vals is not None else None), counts
 
     def histogram(self, hist, keys):
         self.api.atomic_histogram(hist, keys, pol=self.apol, res=self.res)
@@ -134,29 +224,39 @@ def forall_daxpy(rng, a, b, s, ops=None):
 
 
 # ----------------------------------------------------------------------------------------- reductions
-def _allreduce(rng, val, red):
+def _allreduce(rng, val, red, res=None):
     if rng.world > 1:
-        dist.all_reduce(val, op=red, group=rng.group)
+        if rng.comm is not None and res is not None:
+            # one peer-memory all-gather, folded in rank order (deterministic for floating point)
+            g = rng.comm.allgather_small(val, res)
+            op = {dist.ReduceOp.SUM: 0, dist.ReduceOp.MIN: 1, dist.ReduceOp.MAX: 2}[red]
+            val.copy_(_fold(op, g))
+        else:
+            dist.all_reduce(val, op=red, group=rng.group)
     return val
 
 
 def reduce_sum(rng, x, ops=None, as_tensor=False):
-    v = _allreduce(rng, _ops(ops).reduce(_KIND["sum"], x)[0], dist.ReduceOp.SUM)
+    ops = _ops(ops)
+    v = _allreduce(rng, ops.reduce(_KIND["sum"], x)[0], dist.ReduceOp.SUM, getattr(ops, "res", None))
     return v if as_tensor else v.item()
 
 
 def reduce_min(rng, x, ops=None, as_tensor=False):
-    v = _allreduce(rng, _ops(ops).reduce(_KIND["min"], x)[0], dist.ReduceOp.MIN)
+    ops = _ops(ops)
+    v = _allreduce(rng, ops.reduce(_KIND["min"], x)[0], dist.ReduceOp.MIN, getattr(ops, "res", None))
     return v if as_tensor else v.item()
 
 
 def reduce_max(rng, x, ops=None, as_tensor=False):
-    v = _allreduce(rng, _ops(ops).reduce(_KIND["max"], x)[0], dist.ReduceOp.MAX)
+    ops = _ops(ops)
+    v = _allreduce(rng, ops.reduce(_KIND["max"], x)[0], dist.ReduceOp.MAX, getattr(ops, "res", None))
     return v if as_tensor else v.item()
 
 
 def reduce_dot(rng, x, y, ops=None, as_tensor=False, res=None):
-    v = _allreduce(rng, (_ops(ops) if ops is not None or res is None else B200Ops(res)).dot(x, y), dist.ReduceOp.SUM)
+    ops = _ops(ops) if ops is not None or res is None else B200Ops(res)
+    v = _allreduce(rng, ops.dot(x, y), dist.ReduceOp.SUM, getattr(ops, "res", None))
     return v if as_tensor else v.item()
 
 
@@ -199,8 +299,11 @@ def _scan(rng, inclusive, src, dst, op, init, ops, res):
     if rng.world > 1:
         # shard total -> all_gather -> fold of the lower ranks' totals, all on the device
         total = ops.reduce(op, src)[0]  # rb200_reduce_kind SUM/MIN/MAX == rb200_op PLUS/MINIMUM/MAXIMUM
-        totals = torch.empty(rng.world, dtype=src.dtype, device=src.device)
-        dist.all_gather_into_tensor(totals, total, group=rng.group)
+        if rng.comm is not None and getattr(ops, "res", None) is not None:
+            totals = rng.comm.allgather_small(total, ops.res).reshape(rng.world)
+        else:
+            totals = torch.empty(rng.world, dtype=src.dtype, device=src.device)
+            dist.all_gather_into_tensor(totals, total, group=rng.group)
         lower = totals[:rng.rank]
         if rng.rank == 0:
             carry = None
@@ -256,18 +359,27 @@ def _bounds(kview, orig_dtype, n, targets, descending):
     return lo
 
 
-def sort_pairs(rng, keys, vals=None, descending=False, ops=None, res=None, keys_alt=None, vals_alt=None, oversample=32):
-    """Stable sample sort.  keys/vals: this rank's shard (sorted in place locally first).
-    Returns (keys_out, vals_out): this rank's piece of the globally sorted sequence -- rank r holds
-    keys that sort before rank r+1's; piece sizes differ (regular sampling bounds them by ~2n/world)."""
+def sort_pairs(rng, keys, vals=None, descending=False, ops=None, res=None, keys_alt=None, vals_alt=None, oversample=512):
+    """Stable sample sort.  keys/vals: this rank's shard.  Returns (keys_out, vals_out): this rank's
+    piece of the globally sorted sequence -- rank r holds keys that sort before rank r+1's; piece
+    sizes differ with the sampling error (oversample samples per rank and destination).
+
+    One rank: the local sort, in place.  Several: splitters from a regular sample of the UNSORTED
+    shards, one stable splitter partition per rank (a single onesweep pass, rb200_partition_pairs),
+    the all-to-all, and ONE local stable sort of what arrives.  Equal keys always meet on one rank
+    and arrive ordered by (source rank, position in the source shard), so the result is the
+    stable sort of the concatenated shards.  keys_alt / vals_alt: optional scratch of the shard's
+    size (the partition output); keys / vals are left untouched when world > 1."""
     ops = ops if ops is not None else B200Ops(res)
-    ops.sort_pairs(keys, vals, descending, keys_alt, vals_alt)
     if rng.world == 1:
+        ops.sort_pairs(keys, vals, descending, keys_alt, vals_alt)
         return keys, vals
     W, n = rng.world, keys.numel()
+    if W - 1 > 7:
+        raise ValueError("sort_pairs: at most 8 ranks (one node)")
     dev, kdt = keys.device, keys.dtype
     kview = _signed_view(keys)
-    # regular sampling of the locally sorted shard
+    # regular sample of the unsorted shard
     s = W * oversample
     padded = torch.zeros(s, dtype=kview.dtype, device=dev)
     n_samples = min(s, n)
@@ -280,32 +392,41 @@ def sort_pairs(rng, keys, vals=None, descending=False, ops=None, res=None, keys_
     gathered = torch.empty(W * s, dtype=kview.dtype, device=dev)
     dist.all_gather_into_tensor(gathered, padded, group=rng.group)
     valid = (torch.arange(s, device=dev).unsqueeze(0) < all_counts.unsqueeze(1)).reshape(-1)
-    pool = torch.sort(_wide(gathered[valid], kdt), descending=descending, stable=True).values  # <= W*s elements: plumbing
-    m = pool.numel()
+    raw = gathered[valid]
+    order = torch.sort(_wide(raw, kdt), descending=descending, stable=True).indices  # <= W*s elements: plumbing
+    m = raw.numel()
     if m > 0:
-        splitters = pool[(torch.arange(1, W, device=dev, dtype=torch.int64) * m) // W]
-        # a key goes to the rank given by the number of splitters that sort at or before it: equal keys
-        # always meet on one rank, so stability only needs the source-rank order to be kept on arrival
-        bounds = _bounds(kview, kdt, n, splitters, descending)
+        pick = (torch.arange(1, W, device=dev, dtype=torch.int64) * m) // W
+        splitters = raw[order[pick]].cpu().numpy()  # tiny D2H: the splitters are kernel arguments
     else:
-        bounds = torch.zeros(W - 1, dtype=torch.int64, device=dev)
-    edges = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), bounds, torch.tensor([n], dtype=torch.int64, device=dev)])
-    send_counts = (edges[1:] - edges[:-1]).clamp_(min=0)
+        splitters = _signed_view(torch.zeros(0, dtype=kdt)).numpy()
+    if kdt in _SIGNED:
+        splitters = splitters.view({torch.uint32: "uint32", torch.uint64: "uint64"}[kdt])
+    # a key goes to the rank given by the number of splitters that sort at or before it
+    comm = rng.comm if getattr(ops, "res", None) is not None else None
+    if comm is not None and comm.capacity(keys.element_size(), vals.element_size() if vals is not None else 0) >= n + n // 8:
+        # fused partition + all-to-all: the splitter sweep stores every bucket into its destination GPU
+        keys_out, vals_out = comm.exchange_pairs(keys, vals, splitters, descending, ops.res)
+        ops.sort_pairs(keys_out, vals_out, descending, keys_alt if keys_alt is not None and keys_alt.numel() >= keys_out.numel() else None,
+                       vals_alt if vals_alt is not None and vals_out is not None and vals_alt.numel() >= vals_out.numel() else None)
+        return keys_out, vals_out
+    kpart, vpart, bucket_counts = ops.partition_pairs(keys, vals, splitters, descending, keys_alt, vals_alt)
+    send_counts = bucket_counts[:W].to(torch.int64).contiguous()
     recv_counts = torch.empty_like(send_counts)
     dist.all_to_all_single(recv_counts, send_counts, group=rng.group)
     send_l, recv_l = send_counts.tolist(), recv_counts.tolist()  # split sizes are host-side arguments of the collective
     n_out = sum(recv_l)
-    kout = torch.empty(n_out, dtype=kview.dtype, device=dev)
-    dist.all_to_all_single(kout, kview, output_split_sizes=recv_l, input_split_sizes=send_l, group=rng.group)
+    kpv = _signed_view(kpart)
+    kout = torch.empty(n_out, dtype=kpv.dtype, device=dev)
+    dist.all_to_all_single(kout, kpv, output_split_sizes=recv_l, input_split_sizes=send_l, group=rng.group)
     keys_out = kout.view(kdt)
     vals_out = None
     if vals is not None:
-        vview = _signed_view(vals)
-        vout = torch.empty(n_out, dtype=vview.dtype, device=dev)
-        dist.all_to_all_single(vout, vview, output_split_sizes=recv_l, input_split_sizes=send_l, group=rng.group)
+        vpv = _signed_view(vpart)
+        vout = torch.empty(n_out, dtype=vpv.dtype, device=dev)
+        dist.all_to_all_single(vout, vpv, output_split_sizes=recv_l, input_split_sizes=send_l, group=rng.group)
         vals_out = vout.view(vals.dtype)
-    # the received runs arrive concatenated in source-rank order: a STABLE local sort merges them
-    # and keeps (source rank, local position) order among equal keys
+    # the runs arrive concatenated in source-rank order, each in its source order: one stable sort finishes the job
     ops.sort_pairs(keys_out, vals_out, descending, None, None)
     return keys_out, vals_out
 

@@ -77,6 +77,25 @@ class OracleOps:
             self._np(keys)[:] = ok
             self._np(vals)[:] = ov
 
+    def partition_pairs(self, keys, vals, splitters, descending, keys_out=None, vals_out=None):
+        """same contract as rb200_partition_pairs: bucket = number of splitters that sort at or before the key, stable"""
+        k = self._np(keys)
+        sp = np.asarray(splitters, dtype=k.dtype)
+        if sp.size:
+            b = ((k[:, None] <= sp[None, :]) if descending else (k[:, None] >= sp[None, :])).sum(axis=1)
+        else:
+            b = np.zeros(k.size, dtype=np.int64)
+        order = np.argsort(b, kind="stable")
+        counts = torch.zeros(8, dtype=torch.int64)
+        counts[:sp.size + 1] = torch.from_numpy(np.bincount(b, minlength=sp.size + 1).astype(np.int64))
+        ko = keys_out if keys_out is not None else torch.empty_like(keys)
+        self._np(ko)[:] = k[order]
+        vo = None
+        if vals is not None:
+            vo = vals_out if vals_out is not None else torch.empty_like(vals)
+            self._np(vo)[:] = self._np(vals)[order]
+        return ko, vo, counts
+
     def histogram(self, hist, keys):
         hist += torch.from_numpy(self.orc.histogram(keys.numpy(), hist.numel()))
 
@@ -111,9 +130,12 @@ def main():
         return t.view(torch.int32).numpy().view(np.uint32) if t.dtype == torch.uint32 else t.numpy()
 
     checks = 0
-    for n_global in (0, 1, 5, 1000, 20011) if not cuda else (5, 1000, 1 << 20):
+    # on GPUs every path runs twice: exchanges by NCCL collectives, then over the NVLink peer-memory communicator
+    comms = [None, multi.PeerComm(exchange_bytes=32 << 20)] if cuda else [None]
+    for comm, n_global in [(c, n) for c in comms for n in ((0, 1, 5, 1000, 20011) if not cuda else (5, 1000, 1 << 20))]:
         rng_np = np.random.default_rng(1234 + n_global)  # same stream on every rank
         sr = multi.ShardedRange.split(n_global, world, rank)
+        sr.comm = comm
         lo, hi = sr.offset, sr.offset + sr.n_local
         # ---- reductions (int: bit-exact; float: n*eps)
         xi = rng_np.integers(-100, 100, n_global).astype(np.int32)
@@ -177,6 +199,9 @@ def main():
         assert np.array_equal(N(a), orc.triad(b, c, 3.0)[lo:hi])
         checks += 1
     dist.barrier()
+    for c in comms:
+        if c is not None:
+            c.close()
     dist.destroy_process_group()
     print(f"rank {rank}: multi OK ({checks} sizes)")
 

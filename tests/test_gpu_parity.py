@@ -319,6 +319,52 @@ def test_sorts_against_reference_fixtures(rb, t):
 
 
 # ------------------------------------------------------------------ atomics
+def _np_partition(k, v, sp, desc):
+    """stable split restated in numpy: bucket = number of splitters that sort at or before the key"""
+    if len(sp):
+        b = ((k[:, None] <= sp[None, :]) if desc else (k[:, None] >= sp[None, :])).sum(axis=1)
+    else:
+        b = np.zeros(k.size, dtype=np.int64)
+    order = np.argsort(b, kind="stable")
+    return k[order], (v[order] if v is not None else None), np.bincount(b, minlength=8)[:8]
+
+
+@pytest.mark.parametrize("dtype", NP_TYPES)
+@pytest.mark.parametrize("desc", [False, True])
+def test_partition_pairs_is_the_stable_split(rb, dtype, desc):
+    """rb200_partition_pairs (the exchange step of the multi-GPU sample sort): bit-exact against the numpy
+    restatement, keys and values, for 0..7 splitters, ragged sizes, duplicated splitters and keys"""
+    for n, nsplit, vdt in [(1, 1, np.uint32), (33, 0, np.uint32), (1000, 3, np.uint32), (7681, 7, np.uint64), (262144 + 7, 1, np.uint32),
+                           (1_000_003, 7, np.uint32), (50_000, 4, None)]:
+        k = data(dtype, n, 900 + n + nsplit, -50, 50)  # narrow range: many equal keys, keys equal to splitters
+        if np.issubdtype(dtype, np.floating) and n > 4:
+            k[1], k[3] = -0.0, 0.0
+        sp = np.sort(np.random.default_rng(n).choice(k, size=nsplit, replace=True)) if nsplit else np.zeros(0, dtype=dtype)
+        if desc:
+            sp = sp[::-1].copy()
+        v = np.arange(n).astype(vdt) if vdt is not None else None
+        ko = torch.empty_like(dev(k))
+        vo = torch.empty_like(dev(v)) if v is not None else None
+        counts = torch.zeros(8, dtype=torch.int64, device="cuda")
+        rb.partition_pairs(dev(k), ko, dev(v) if v is not None else None, vo, sp, counts, int(desc))
+        ek, ev, ec = _np_partition(k, v, sp, desc)
+        assert np.array_equal(host(counts), ec), (n, nsplit)
+        assert np.array_equal(host(ko).view(np.uint8), ek.view(np.uint8)), (n, nsplit)  # bit patterns: -0.0 stays -0.0
+        if v is not None:
+            assert np.array_equal(host(vo), ev), (n, nsplit)
+
+
+def test_partition_pairs_rejects_bad_arguments(rb):
+    k = dev(np.arange(10, dtype=np.uint32))
+    counts = torch.zeros(8, dtype=torch.int64, device="cuda")
+    with pytest.raises(rb.B200Error):  # splitters out of order
+        rb.partition_pairs(k, torch.empty_like(k), None, None, np.array([5, 3], dtype=np.uint32), counts)
+    with pytest.raises(rb.B200Error):  # in place is not supported
+        rb.partition_pairs(k, k, None, None, np.array([5], dtype=np.uint32), counts)
+    with pytest.raises(rb.B200Error):  # more than 7 splitters
+        rb.partition_pairs(k, torch.empty_like(k), None, None, np.arange(8, dtype=np.uint32), counts)
+
+
 @pytest.mark.parametrize("aggregate", [False, True])
 def test_atomic_histogram_and_pi(rb, orc, aggregate):
     rng = np.random.default_rng(19)
