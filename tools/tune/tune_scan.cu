@@ -108,10 +108,32 @@ template <class T> void run_type(const char* tname, long long n)
   cudaFree(in); cudaFree(out); cudaFree(ref); cudaFree(ws); cudaFree(tmp); cudaFree(bad);
 }
 
+// diagnostic operator: double-typed scan whose combine is an INTEGER add on the bit patterns -- same loads,
+// stores, shuffles and tile-state traffic as Plus<double>, but no FP64 instruction (results are meaningless)
+struct BitAdd {
+  using value_type = double;
+  __host__ __device__ static double identity() { return 0.0; }
+  __device__ double operator()(double a, double b) const { return __longlong_as_double(__double_as_longlong(a) + __double_as_longlong(b)); }
+};
+void run_bitadd(long long n)
+{
+  double *in, *out;
+  CK(cudaMalloc(&in, n * 8)); CK(cudaMalloc(&out, n * 8));
+  fill_kernel<<<1184, 256>>>(in, n, 12345u);
+  void* ws; CK(cudaMalloc(&ws, 64 << 20));
+  using S = scan::Shape<384, 7, 10, 5, 0>;
+  float ms = time_ms([&] { CK((scan::launch<double, BitAdd, true, S>(0, in, out, n, 0.0, ws, g_clear, g_set))); }, 5);
+  printf("f64  BitAdd (integer add on the bits) BLOCK=384 VPT=7 : %8.4f ms %8.1f GB/s\n", ms, 16.0 * n / ms / 1e6);
+  ms = time_ms([&] { CK((scan::launch<double, Plus<double>, true, S>(0, in, out, n, 0.0, ws, g_clear, g_set))); }, 5);
+  printf("f64  Plus<double>                     BLOCK=384 VPT=7 : %8.4f ms %8.1f GB/s\n", ms, 16.0 * n / ms / 1e6);
+  cudaFree(in); cudaFree(out); cudaFree(ws);
+}
+
 int main(int argc, char** argv)
 {
   int log2n = argc > 1 ? atoi(argv[1]) : 28;
   long long n = 1ll << log2n;
+  if (argc > 2) { run_bitadd(n); return 0; }
   run_type<int>("i32", n);
   run_type<long long>("i64", n);
   run_type<double>("f64", n);  // integer-valued doubles: every association gives the same bits, so CUB still checks it
