@@ -291,8 +291,8 @@ B200_D void prefetch_l2(const void* first, const void* last)
 // MATCH 0 = ballot loop / 1 = match.any / 2 = shared-memory atomicOr masks.
 template <int BLOCK_, int ITEMS_, int MIN_CTAS_, int MATCH_ = 0, bool PACK_ = false, int PREFETCH_ = 0, int LB_WARPS_ = 2, int LB_BATCH_ = 8, int LB_SLEEP_ = 400>
 struct SweepShape {
-  // late-count kernel: predecessor tiles in flight per look-back lane (32-bit counters), and the
-  // back-off in ns when the nearest predecessor has not published yet
+  // late-count kernel: half the number of predecessor tiles in flight per look-back lane (n < 2^30;
+  // LB_BATCH itself above), and the back-off in ns when the nearest predecessor has not published yet
   static constexpr int LB_BATCH = LB_BATCH_, LB_SLEEP = LB_SLEEP_;
   static constexpr int BLOCK = BLOCK_, ITEMS = ITEMS_, MIN_CTAS = MIN_CTAS_, MATCH = MATCH_;
   static constexpr bool PACK = PACK_;
@@ -635,7 +635,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
                      const VT* __restrict__ vals_in, VT* __restrict__ vals_out,
                      const long long n,
                      const unsigned long long* __restrict__ bin_base,  // [256] of this pass
-                     C* lookback,                                      // [ntiles][256], zero on entry
+                     C* lookback,                                      // [ntiles][256] inclusive prefixes, then [ntiles][256] u16 tile counts; zero on entry
                      unsigned* ticket,                                 // zero on entry
                      const DigitFn digit)
 {
@@ -646,6 +646,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
   constexpr bool HAS_VALUES = SM::HAS_VALUES, PACK = SM::PACK;
   static_assert(ITEMS % 2 == 0, "ranks are kept two per register");
   static_assert(S::MATCH == 3, "late-count kernel: ballot match");
+  static_assert(TILE < 65535, "tile counts are published as 16-bit words (count + 1)");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM& s = *reinterpret_cast<SM*>(smem_raw);
 
@@ -659,6 +660,12 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
   const int tile_count = (int)((n - tile_base) < (long long)TILE ? (n - tile_base) : (long long)TILE);
   const bool full = (tile_count == TILE);
   const int wofs = w * (WARP * ITEMS);  // this warp's first item within the tile
+  // Look-back words.  A tile publishes its digit counts as 16-bit words (count + 1; 0 = not yet) in
+  // local16 right after the ranking, and its inclusive prefixes (value | GLOBAL) in `lookback` once
+  // its own look-back is done.  16-bit counts let a look-back lane keep 16 predecessors in flight in
+  // the registers 8 took before: the rate at which finished prefixes propagate from tile to tile
+  // (predecessors consumed per L2 round trip) is what bounds the pass, not HBM or the LSU.
+  uint16_t* const local16 = reinterpret_cast<uint16_t*>(lookback + ((n + TILE - 1) / TILE) * RADIX);
 
   U key[ITEMS];            // warp-striped: item (j, l) is tile item wofs + j*32 + l
   uint32_t rp[ITEMS / 2];  // two 16-bit ranks per register: warp-local first, tile ranks later
@@ -714,7 +721,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
     uint32_t cnt = 0;
 #pragma unroll
     for (int i = 0; i < NW; ++i) cnt += s.cnt[i][tid];
-    st_lookback(lookback + tile * RADIX + tid, (C)cnt | (tile == 0 ? F::GLOBAL : F::LOCAL));
+    local16[tile * RADIX + tid] = (uint16_t)(cnt + 1);
     s.count[tid] = (uint16_t)cnt;
     uint32_t incl = cnt;
 #pragma unroll
@@ -787,51 +794,80 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
       }
     }
   } else {
-    // look-back warps: lane owns D consecutive digits; batched decoupled look-back, one 128-bit
-    // load = 4 digits of one predecessor tile, B predecessors in flight per lane
-    constexpr int NQ = RADIX / (LBT * 4);  // quads per lane: 1 (two look-back warps) or 2 (one)
+    // look-back warps: lane owns D consecutive digits.  Per round trip: the 16-bit counts of B
+    // predecessors (one 8-byte load = 4 digits of one tile) plus the finished prefixes of the
+    // predecessors at checkpoints CK0 and CK1 of the batch; the walk ends at the first checkpoint
+    // whose prefix is there (or at tile 0), adding the counts of the tiles in between.
+    constexpr int NQ = RADIX / (LBT * 4);  // groups of 4 digits per lane: 1 (two look-back warps) or 2 (one)
     constexpr int D = 4 * NQ;
     const int q = (tid - BLOCK) * D;
     C prev[D] = {};
     if (tile != 0) {
-      constexpr int B = (sizeof(C) == 4 ? S::LB_BATCH : S::LB_BATCH / 2) / NQ;
-      bool done[D] = {};
+      constexpr int B = (sizeof(C) == 4 ? 2 : 1) * S::LB_BATCH / NQ;
+      constexpr int CK0 = B / 2 - 1, CK1 = B - 1;
       long long p = tile - 1;
       while (true) {
-        Quad<C> v[B][NQ];
+        uint2 v[B][NQ];
+        Quad<C> g0[NQ], g1[NQ];
 #pragma unroll
         for (int b = 0; b < B; ++b)
 #pragma unroll
           for (int k = 0; k < NQ; ++k) {
-            if (p - b >= 0) v[b][k] = ld_quad(lookback + (p - b) * RADIX + q + 4 * k);
-            else v[b][k] = Quad<C>{{F::GLOBAL, F::GLOBAL, F::GLOBAL, F::GLOBAL}};  // before the first tile: zero, final
+            v[b][k] = make_uint2(0u, 0u);
+            if (p - b >= 0) {
+              const unsigned long long w64 = ld_relaxed_u64(reinterpret_cast<const uint64_t*>(local16 + (p - b) * RADIX + q + 4 * k));
+              v[b][k] = make_uint2((uint32_t)w64, (uint32_t)(w64 >> 32));
+            }
           }
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+          g0[k] = Quad<C>{{0, 0, 0, 0}};
+          g1[k] = Quad<C>{{0, 0, 0, 0}};
+          if (p - CK0 >= 0) g0[k] = ld_quad(lookback + (p - CK0) * RADIX + q + 4 * k);
+          if (p - CK1 >= 0) g1[k] = ld_quad(lookback + (p - CK1) * RADIX + q + 4 * k);
+        }
         int consumed = 0;
         bool all_done = false;
 #pragma unroll
         for (int b = 0; b < B; ++b) {
           if (all_done) break;
-          bool ok = true;
+          if (p - b < 0) {  // walked past tile 0: everything before is counted
+            all_done = true;
+            break;
+          }
+          if (b == CK0 || b == CK1) {
+            bool ready = true;
 #pragma unroll
-          for (int c = 0; c < D; ++c) ok = ok && (done[c] || (v[b][c >> 2].v[c & 3] & ~F::MASK) != 0);
-          if (!__all_sync(FULL_MASK, ok)) break;  // a predecessor has not published yet: re-poll from here
+            for (int c = 0; c < D; ++c) ready = ready && (((b == CK0 ? g0 : g1)[c >> 2].v[c & 3] & F::GLOBAL) != 0);
+            if (__all_sync(FULL_MASK, ready)) {
 #pragma unroll
-          for (int c = 0; c < D; ++c) {
-            if (!done[c]) {
-              prev[c] += v[b][c >> 2].v[c & 3] & F::MASK;
-              if (v[b][c >> 2].v[c & 3] & F::GLOBAL) done[c] = true;
+              for (int c = 0; c < D; ++c) prev[c] += (b == CK0 ? g0 : g1)[c >> 2].v[c & 3] & F::MASK;
+              all_done = true;
+              break;
             }
           }
-          ++consumed;
-          bool mine = true;
+          uint32_t e[D];
 #pragma unroll
-          for (int c = 0; c < D; ++c) mine = mine && done[c];
-          all_done = __all_sync(FULL_MASK, mine);
+          for (int k = 0; k < NQ; ++k) {
+            e[4 * k + 0] = v[b][k].x & 0xffffu;
+            e[4 * k + 1] = v[b][k].x >> 16;
+            e[4 * k + 2] = v[b][k].y & 0xffffu;
+            e[4 * k + 3] = v[b][k].y >> 16;
+          }
+          bool ok = true;
+#pragma unroll
+          for (int c = 0; c < D; ++c) ok = ok && (e[c] != 0);
+          if (!__all_sync(FULL_MASK, ok)) break;  // this predecessor has not published its counts yet: re-poll from here
+#pragma unroll
+          for (int c = 0; c < D; ++c) prev[c] += (C)(e[c] - 1);
+          ++consumed;
         }
         if (all_done) break;
         p -= consumed;
         if (consumed < B) __nanosleep(consumed == 0 ? S::LB_SLEEP : S::LB_SLEEP / 4);  // leave the issue slots to the scatter
       }
+    }
+    {
 #pragma unroll
       for (int k = 0; k < NQ; ++k) {
         Quad<C> g;
@@ -895,7 +931,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 template <class U, class VT> struct Tuning {
   static constexpr int VB = std::is_same<VT, NoValue>::value ? 0 : (int)sizeof(VT);
   static constexpr int ITEMS = sizeof(U) == 4 ? (VB <= 4 ? 30 : 20) : (VB == 0 ? 18 : (VB == 4 ? 16 : 14));
-  using shape = SweepShape<256, ITEMS, 3, 3, false, 300>;
+  using shape = SweepShape<256, ITEMS, 3, 3, false, 300, 2, 4>;
 };
 
 template <class U, class VT, class S = typename Tuning<U, VT>::shape> inline long long num_tiles(long long n)
@@ -909,7 +945,7 @@ template <class U, class VT, class S = typename Tuning<U, VT>::shape> inline siz
   constexpr int NPASS = sizeof(U);
   size_t header = (size_t)NPASS * RADIX * 8 * 2 + 256;
   size_t cbytes = (n < (1ll << 30)) ? 4 : 8;
-  return header + (size_t)num_tiles<U, VT, S>(n) * RADIX * cbytes;
+  return header + (size_t)num_tiles<U, VT, S>(n) * RADIX * (cbytes + 2);  // inclusive prefixes + 16-bit tile counts
 }
 
 // opt-in to > 48 KB of dynamic shared memory, once per kernel (keyed on the kernel itself:
@@ -975,7 +1011,7 @@ inline cudaError_t sort(cudaStream_t stream, U* keys, U* keys_alt, VT* vals, VT*
   unsigned* tickets = (unsigned*)(bin_base + NPASS * RADIX);
   void* lookback = (char*)workspace + header;
   const bool small = n < (1ll << 30);
-  const size_t lb_bytes = (size_t)num_tiles<U, VT, S>(n) * RADIX * (small ? 4 : 8);
+  const size_t lb_bytes = (size_t)num_tiles<U, VT, S>(n) * RADIX * ((small ? 4 : 8) + 2);
 
   cudaError_t e = cudaMemsetAsync(workspace, 0, header + lb_bytes, stream);
   if (e != cudaSuccess) return e;
@@ -1042,7 +1078,7 @@ template <class U, class VT> struct PartitionTuning {
   // the three digit evaluations per key inside the register budget
   static constexpr int VB = std::is_same<VT, NoValue>::value ? 0 : (int)sizeof(VT);
   static constexpr int ITEMS = sizeof(U) == 4 ? (VB <= 4 ? 24 : 16) : (VB == 0 ? 14 : 12);
-  using shape = SweepShape<256, ITEMS, 3, 3, false, 300>;
+  using shape = SweepShape<256, ITEMS, 3, 3, false, 300, 2, 4>;
 };
 
 // workspace: same layout as sort's ([ghist 256 u64 x NPASS][bin_base ...][tickets][lookback]); only pass 0 is used
@@ -1060,7 +1096,7 @@ inline cudaError_t bucket_counts(cudaStream_t stream, const U* keys_in, long lon
   unsigned long long* ghist = (unsigned long long*)workspace;
   const bool small = n < (1ll << 30);
   const long long ntiles = num_tiles<U, VT, S>(n > 0 ? n : 1);
-  const size_t lb_bytes = (size_t)ntiles * RADIX * (small ? 4 : 8);
+  const size_t lb_bytes = (size_t)ntiles * RADIX * ((small ? 4 : 8) + 2);
   cudaError_t e = cudaMemsetAsync(workspace, 0, header + lb_bytes, stream);
   if (e != cudaSuccess) return e;
   if (n > 0) {

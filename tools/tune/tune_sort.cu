@@ -87,8 +87,8 @@ template <class S> void run_shape(const Bufs& b)
   int occ = 0;
   using KK = rsort::SweepKernel<K, V, false, uint32_t, S>;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KK::kernel(), S::THREADS, sizeof(typename KK::SM));
-  printf("BLOCK=%4d ITEMS=%2d MIN_CTAS=%d MATCH=%d PACK=%d PREFETCH=%3d LBW=%d tile=%5d smem=%6.1fKB occ=%d : %8.3f ms  %6.2f Gkeys/s  model%.0f %7.1f GB/s %s\n", S::BLOCK, S::ITEMS,
-         S::MIN_CTAS, S::MATCH, (int)S::PACK, S::PREFETCH_TILES, S::LB_WARPS, S::TILE, sizeof(typename KK::SM) / 1024.0, occ, ms, b.n / ms / 1e6, MODEL_BYTES, MODEL_BYTES * b.n / ms / 1e6,
+  printf("BLOCK=%4d ITEMS=%2d MIN_CTAS=%d MATCH=%d PACK=%d PREFETCH=%3d LBW=%d LBB=%d tile=%5d smem=%6.1fKB occ=%d : %8.3f ms  %6.2f Gkeys/s  model%.0f %7.1f GB/s %s\n", S::BLOCK, S::ITEMS,
+         S::MIN_CTAS, S::MATCH, (int)S::PACK, S::PREFETCH_TILES, S::LB_WARPS, S::LB_BATCH, S::TILE, sizeof(typename KK::SM) / 1024.0, occ, ms, b.n / ms / 1e6, MODEL_BYTES, MODEL_BYTES * b.n / ms / 1e6,
          h ? "MISMATCH" : "ok");
   fflush(stdout);
 }
@@ -129,6 +129,12 @@ int main(int argc, char** argv)
 #if TK == 0
   run_shape<rsort::SweepShape<384, 24, 2, 2>>(b);
   run_shape<rsort::SweepShape<256, 30, 3, 3, false, 300>>(b);
+  run_shape<rsort::SweepShape<256, 30, 3, 3, false, 300, 2, 4>>(b);
+  run_shape<rsort::SweepShape<256, 30, 3, 3, false, 300, 2, 12>>(b);
+  run_shape<rsort::SweepShape<256, 30, 3, 3, false, 300, 1, 8>>(b);
+  run_shape<rsort::SweepShape<256, 32, 3, 3, false, 300, 1, 8>>(b);
+  run_shape<rsort::SweepShape<384, 24, 2, 3, false, 200>>(b);
+  run_shape<rsort::SweepShape<256, 24, 3, 3, false, 400>>(b);
 #elif TK == 1
   run_shape<rsort::SweepShape<384, 24, 2, 2>>(b);
   run_shape<rsort::SweepShape<256, 30, 3, 3, false, 300>>(b);
