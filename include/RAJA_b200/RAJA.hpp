@@ -5,6 +5,7 @@
 //
 //     RAJA::b200_exec<BLOCK, Async=false>, RAJA::b200_exec_async<BLOCK>
 //     RAJA::b200_reduce                     (classic ReduceSum/Min/Max/MinLoc/MaxLoc objects)
+//     RAJA::b200_multi_reduce               (MultiReduceSum/Min/Max/BitOr/BitAnd: run-time indexed bins)
 //     RAJA::b200_atomic                     (atomicAdd & friends)
 //     RAJA::b200_synchronize
 //     RAJA::b200::{device,device_zeroed,pinned}_mempool_type
@@ -74,5 +75,6 @@
 // ---- 4. everything found by ADL -----------------------------------------------------------------
 #include "RAJA_b200/forall.hpp"
 #include "RAJA_b200/reduce.hpp"
+#include "RAJA_b200/multi_reduce.hpp"
 
 #endif  // RAJA_B200_RAJA_HPP

@@ -78,12 +78,16 @@ forall_impl(resources::Cuda res, b200_exec<BLOCK_SIZE, Async> const& pol, Iterab
       // classic reducer objects captured by the body set themselves up for this launch when the body
       // is copied -- exactly once, inside the scope (RAJA_b200/reduce_classic.hpp); later copies (the
       // by-value kernel argument) just alias that set-up
+      size_t dyn_smem = 0;  // what multi-reducers in the body reserved (RAJA_b200/multi_reduce.hpp)
       auto make_body = [&]() {
         RAJA::b200_detail::LaunchScope scope(info.grid, stream);
-        return BodyT {loop_body, begin, f_params};
+        BodyT b {loop_body, begin, f_params};
+        dyn_smem = RAJA::b200_detail::tl_launch().dyn_smem;
+        return b;
       };
       BodyT body = make_body();
-      RAJA::b200_detail::check(::b200::launch_forall<(int)BLOCK_SIZE, UNROLL, IndexType>(stream, body, len, FinT {}, info.grid), "forall launch");
+      RAJA::b200_detail::check(::b200::launch_forall<(int)BLOCK_SIZE, UNROLL, IndexType>(stream, body, len, FinT {}, info.grid, "forall_kernel", dyn_smem),
+                               "forall launch");
     }
     if constexpr (!empty) RAJA::expt::ParamMultiplexer::parampack_resolve(pol, f_params, info);
     if (!Async) res.wait();

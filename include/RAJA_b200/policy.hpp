@@ -115,6 +115,7 @@ struct LaunchRecord
   bool active         = false;
   int grid            = 0;
   cudaStream_t stream = 0;
+  size_t dyn_smem     = 0;  // dynamic shared memory reserved so far by objects captured in the body (multi-reducers)
 };
 inline LaunchRecord& tl_launch()
 {
@@ -126,9 +127,10 @@ struct LaunchScope
   LaunchScope(int grid, cudaStream_t s)
   {
     LaunchRecord& r = tl_launch();
-    r.active = true;
-    r.grid   = grid;
-    r.stream = s;
+    r.active   = true;
+    r.grid     = grid;
+    r.stream   = s;
+    r.dyn_smem = 0;
   }
   ~LaunchScope() { tl_launch().active = false; }
 };

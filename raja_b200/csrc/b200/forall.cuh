@@ -100,11 +100,12 @@ inline int forall_grid(Index len)
 
 template <int BLOCK, int UNROLL, class Index, class Body, class Finalize>
 inline cudaError_t launch_forall(cudaStream_t stream, const Body& body, Index len, const Finalize& fin, int grid,
-                                 const char* name = "forall_kernel")
+                                 const char* name = "forall_kernel", size_t dyn_smem = 0)
 {
   LaunchScope scope(name, stream);
   if (len < 0) return cudaErrorInvalidValue;  // len == 0 still launches: the body may own tail work
-  forall_kernel<BLOCK, UNROLL, Index, Body, Finalize><<<grid, BLOCK, 0, stream>>>(body, len, fin);
+  // dyn_smem (<= 48 KB): shared memory objects captured in the body asked for (multi-reducer bins)
+  forall_kernel<BLOCK, UNROLL, Index, Body, Finalize><<<grid, BLOCK, dyn_smem, stream>>>(body, len, fin);
   return cudaGetLastError();
 }
 

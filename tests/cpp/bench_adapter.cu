@@ -118,6 +118,19 @@ int main(int argc, char** argv)
     const int reps = bins == 256 ? 2 : 5;
     row(name, "b200_exec + b200_atomic", 4.0 * N, best_ms(s, [&] { RAJA::forall<B>(res, seg, [=] RAJA_DEVICE(long i) { RAJA::atomicAdd<RAJA::b200_atomic>(&hist[keys[i]], 1); }); }, reps, 1));
     row(name, "cuda_exec + cuda_atomic", 4.0 * N, best_ms(s, [&] { RAJA::forall<C>(res, seg, [=] RAJA_DEVICE(long i) { RAJA::atomicAdd<RAJA::cuda_atomic>(&hist[keys[i]], 1); }); }, reps, 1));
+    // the same histogram as a MultiReduceSum (the framework-visible form: bins privatised per CTA in shared memory)
+    snprintf(name, sizeof name, "MultiReduceSum histogram, %d bins", bins);
+    {
+      RAJA::MultiReduceSum<RAJA::b200_multi_reduce, int> mr((size_t)bins);
+      row(name, "b200_exec + b200_multi_reduce", 4.0 * N, best_ms(s, [&] { RAJA::forall<B>(res, seg, [=] RAJA_DEVICE(long i) { mr[keys[i]] += 1; }); }, 5, 1));
+      long long tot = 0;
+      for (int b = 0; b < bins; ++b) tot += mr.get(b);
+      if (tot != 6 * (long long)N) printf("MultiReduceSum(b200) total %lld != %lld\n", tot, 6 * (long long)N);
+    }
+    {
+      RAJA::MultiReduceSum<RAJA::cuda_multi_reduce_atomic, int> mr((size_t)bins);
+      row(name, "cuda_exec + cuda_multi_reduce_atomic", 4.0 * N, best_ms(s, [&] { RAJA::forall<C>(res, seg, [=] RAJA_DEVICE(long i) { mr[keys[i]] += 1; }); }, 5, 1));
+    }
   }
   CK(cudaDeviceSynchronize());
   return 0;
