@@ -100,6 +100,18 @@ RAJA_INLINE void synchronize_impl(const b200_synchronize&) { RAJA::b200_detail::
 
 }  // namespace b200
 }  // namespace policy
+
+namespace resources
+{
+// TypedIndexSet foralls (ExecPolicy<seq_segit, b200_exec<...>>) run on a Cuda resource; the per-segment
+// dispatch is the generic one (pattern/forall.hpp:279-299 -> CallForall -> ADL forall_impl above).
+// Mirrors util/resource.hpp:95-113.
+template<typename ISetIter, size_t BLOCK_SIZE, bool Async>
+struct get_resource<ExecPolicy<ISetIter, ::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async>>>
+{
+  using type = camp::resources::Cuda;
+};
+}  // namespace resources
 }  // namespace RAJA
 
 #endif

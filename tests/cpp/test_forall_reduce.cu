@@ -183,6 +183,40 @@ void test_list_segment_and_empty()
   cudaFree(dx);
 }
 
+void test_index_set()
+{
+  // TypedIndexSet of range and list segments, one b200 launch per segment (seq_segit), classic reducers
+  // (test/functional/forall/indexset-view, reduce-basic: same bodies under seq_exec and b200_exec)
+  using ISet = RAJA::TypedIndexSet<RAJA::TypedRangeSegment<int>, RAJA::TypedListSegment<int>>;
+  const int N = 6000;
+  std::vector<int> x(N);
+  for (int i = 0; i < N; ++i) x[i] = (i * 7) % 23 - 11;
+  std::vector<int> idx;
+  for (int i = 1000; i < 2000; i += 3) idx.push_back(i);
+  RAJA::resources::Cuda res;
+  RAJA::resources::Host hres;
+  ISet iset, hset;
+  iset.push_back(RAJA::TypedRangeSegment<int>(0, 1000));
+  iset.push_back(RAJA::TypedListSegment<int>(idx.data(), idx.size(), res));
+  iset.push_back(RAJA::TypedRangeSegment<int>(2000, N));
+  hset.push_back(RAJA::TypedRangeSegment<int>(0, 1000));
+  hset.push_back(RAJA::TypedListSegment<int>(idx.data(), idx.size(), hres));
+  hset.push_back(RAJA::TypedRangeSegment<int>(2000, N));
+  int* dx = to_dev(x);
+  std::vector<int> y(N, -1), yref(N, -1);
+  int* dy = to_dev(y);
+  RAJA::ReduceSum<RAJA::b200_reduce, long> s(0);
+  RAJA::ReduceMin<RAJA::b200_reduce, int> mn(1 << 30);
+  RAJA::ReduceSum<RAJA::seq_reduce, long> rs(0);
+  RAJA::ReduceMin<RAJA::seq_reduce, int> rmn(1 << 30);
+  RAJA::forall<RAJA::ExecPolicy<RAJA::seq_segit, EXEC>>(iset, [=] RAJA_DEVICE(int i) { s += dx[i]; mn.min(dx[i] * 3); dy[i] = 2 * dx[i]; });
+  RAJA::forall<RAJA::ExecPolicy<RAJA::seq_segit, RAJA::seq_exec>>(hset, [=, &x, &yref](int i) { rs += x[i]; rmn.min(x[i] * 3); yref[i] = 2 * x[i]; });
+  EXPECT(s.get() == rs.get());
+  EXPECT(mn.get() == rmn.get());
+  EXPECT(to_host(dy, N) == yref);
+  cudaFree(dx); cudaFree(dy);
+}
+
 int main()
 {
   for (long N : {1L, 37L, 1000L, 100003L, 3000017L}) {
@@ -192,6 +226,7 @@ int main()
     test_dot(N);
   }
   test_list_segment_and_empty();
+  test_index_set();
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 2; }
   printf(g_fail ? "test_forall_reduce: %d FAILED\n" : "test_forall_reduce: OK\n", g_fail);
