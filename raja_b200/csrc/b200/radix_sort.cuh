@@ -806,7 +806,13 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
       constexpr int B = (sizeof(C) == 4 ? 2 : 1) * S::LB_BATCH / NQ;
       constexpr int CK0 = B / 2 - 1, CK1 = B - 1;
       long long p = tile - 1;
+#ifdef RB200_LB_TRACE
+      unsigned lb_rounds = 0;
+#endif
       while (true) {
+#ifdef RB200_LB_TRACE
+        ++lb_rounds;
+#endif
         uint2 v[B][NQ];
         Quad<C> g0[NQ], g1[NQ];
 #pragma unroll
@@ -862,7 +868,17 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
           for (int c = 0; c < D; ++c) prev[c] += (C)(e[c] - 1);
           ++consumed;
         }
-        if (all_done) break;
+        if (all_done) {
+#ifdef RB200_LB_TRACE
+          if (tid == BLOCK) {  // ticket[8..11]: rounds, depth, max depth, tiles
+            atomicAdd(ticket + 8, lb_rounds);
+            atomicAdd(ticket + 9, (unsigned)(tile - 1 - p + consumed));
+            atomicMax(ticket + 10, (unsigned)(tile - 1 - p + consumed));
+            atomicAdd(ticket + 11, 1u);
+          }
+#endif
+          break;
+        }
         p -= consumed;
         if (consumed < B) __nanosleep(consumed == 0 ? S::LB_SLEEP : S::LB_SLEEP / 4);  // leave the issue slots to the scatter
       }
