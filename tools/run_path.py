@@ -82,5 +82,68 @@ elif a.path in ("hist256", "hist64k", "hist256agg", "hist64kagg"):
     keys = torch.randint(0, nb, (n,), dtype=torch.int32, device="cuda", generator=g)
     hist = torch.zeros(nb, dtype=torch.int32, device="cuda")
     timed(lambda i: rb.atomic_histogram(hist, keys, aggregate=a.path.endswith("agg"), pol=pol), 4)
+elif a.path in ("dotf32", "sumi32", "minloc64"):
+    if a.path == "dotf32":
+        x = torch.rand(n, dtype=torch.float32, device="cuda", generator=g) + 0.5
+        y = torch.rand(n, dtype=torch.float32, device="cuda", generator=g) + 0.5
+        timed(lambda i: rb.reduce_dot(x, y), 8)
+    elif a.path == "sumi32":
+        x = torch.randint(-100, 100, (n,), dtype=torch.int32, device="cuda", generator=g)
+        timed(lambda i: rb.reduce_sum(x), 4)
+    else:
+        x = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+        timed(lambda i: rb.reduce_maxloc(x), 8)
+elif a.path in ("triadf32", "daxpyf32"):
+    b = torch.rand(n, dtype=torch.float32, device="cuda", generator=g)
+    c = torch.rand(n, dtype=torch.float32, device="cuda", generator=g)
+    aa = torch.zeros_like(b)
+    if a.path == "triadf32":
+        timed(lambda i: rb.forall_triad(aa, b, c, 3.0, pol=pol), 12)
+    else:
+        timed(lambda i: rb.forall_daxpy(aa, b, 3.0, pol=pol), 12)
+elif a.path in ("exscan", "inplacescan64", "maxscanf32", "exscanf64"):
+    if a.path == "exscan":
+        x = torch.randint(0, 8, (n,), dtype=torch.int32, device="cuda", generator=g)
+        out = torch.empty_like(x)
+        timed(lambda i: rb.exclusive_scan(x, out, init=5, pol=pol), 8)
+    elif a.path == "inplacescan64":
+        x = torch.randint(-1000, 1000, (n,), dtype=torch.int64, device="cuda", generator=g)
+        timed(lambda i: rb.inclusive_scan_inplace(x, pol=pol), 16)
+    elif a.path == "maxscanf32":
+        x = torch.rand(n, dtype=torch.float32, device="cuda", generator=g)
+        out = torch.empty_like(x)
+        timed(lambda i: rb.inclusive_scan(x, out, op=rb.operators.maximum, pol=pol), 8)
+    else:
+        x = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
+        out = torch.empty_like(x)
+        timed(lambda i: rb.exclusive_scan(x, out, pol=pol), 16)
+elif a.path in ("sortkeys", "sortdesc", "sorti64pairs"):
+    sets = []
+    for i in range(a.reps + 1):
+        if a.path == "sorti64pairs":
+            k = torch.randint(-2**62, 2**62, (n,), dtype=torch.int64, device="cuda", generator=g)
+            sets.append((k, torch.arange(n, dtype=torch.int32, device="cuda").view(torch.uint32)))
+        else:
+            k = torch.randint(-2**31, 2**31, (n,), dtype=torch.int64, device="cuda", generator=g).to(torch.int32).view(torch.uint32)
+            sets.append((k, torch.arange(n, dtype=torch.int32, device="cuda").view(torch.uint32)))
+    if a.path == "sortkeys":
+        timed(lambda i: rb.stable_sort(sets[i][0], pol=pol), 36)
+    elif a.path == "sortdesc":
+        timed(lambda i: rb.sort_pairs(sets[i][0], sets[i][1], rb.operators.greater, pol=pol), 68)
+    else:
+        timed(lambda i: rb.stable_sort_pairs(sets[i][0], sets[i][1], pol=pol), 200)
+elif a.path in ("histzipf", "pi"):
+    if a.path == "pi":
+        # examples/pi-reduce_vs_atomic.cpp with num_bins = n: one atomicAdd on ONE address per iteration (no memory traffic: Gupdates/s)
+        import time
+        rb.atomic_pi(1 << 20)
+        t0 = time.perf_counter(); v = rb.atomic_pi(n); dt = time.perf_counter() - t0
+        print(f"pi: {dt*1e3:.3f} ms  {n/dt/1e9:.2f} Gupdates/s  value {v:.12f}")
+    else:
+        # Zipf-like skew over 65536 bins: bin = floor(65536 * u^4)
+        u = torch.rand(n, dtype=torch.float32, device="cuda", generator=g)
+        keys = (65536 * u ** 4).to(torch.int32).clamp_(0, 65535)
+        hist = torch.zeros(65536, dtype=torch.int32, device="cuda")
+        timed(lambda i: rb.atomic_histogram(hist, keys, pol=pol), 4)
 else:
     raise SystemExit("unknown path")
