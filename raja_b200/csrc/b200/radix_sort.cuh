@@ -289,10 +289,12 @@ B200_D void prefetch_l2(const void* first, const void* last)
 // Compile-time shape of the sweep kernel: BLOCK compute threads (+ 64 look-back threads),
 // ITEMS keys per compute thread, MIN_CTAS resident CTAs per SM the register budget is cut for,
 // MATCH 0 = ballot loop / 1 = match.any / 2 = shared-memory atomicOr masks.
-template <int BLOCK_, int ITEMS_, int MIN_CTAS_, int MATCH_ = 0, bool PACK_ = false, int PREFETCH_ = 0, int LB_WARPS_ = 2, int LB_BATCH_ = 8, int LB_SLEEP_ = 400>
+template <int BLOCK_, int ITEMS_, int MIN_CTAS_, int MATCH_ = 0, bool PACK_ = false, int PREFETCH_ = 0, int LB_WARPS_ = 2, int LB_BATCH_ = 8, int LB_SLEEP_ = 400,
+          int LB_GROUP_ = 8>
 struct SweepShape {
-  // late-count kernel: half the number of predecessor tiles in flight per look-back lane (n < 2^30;
-  // LB_BATCH itself above), and the back-off in ns when the nearest predecessor has not published yet
+  static constexpr int LB_GROUP = LB_GROUP_;  // late-count kernel: tiles per look-back group
+  // late-count kernel: group words in flight per look-back lane and round trip, and (x4) the back-off
+  // in ns when a round made no progress
   static constexpr int LB_BATCH = LB_BATCH_, LB_SLEEP = LB_SLEEP_;
   static constexpr int BLOCK = BLOCK_, ITEMS = ITEMS_, MIN_CTAS = MIN_CTAS_, MATCH = MATCH_;
   static constexpr bool PACK = PACK_;
@@ -608,7 +610,8 @@ template <class U, class VT> struct PeerSplitDigit : SplitDigit<U> {
 //     wavefronts per 32 keys instead of 37;
 //   * the keys of the tile PREFETCH_TILES ahead (about one tile-lifetime) and this tile's values
 //     are pulled toward L2 by bulk prefetches issued from the otherwise idle look-back warps;
-//   * the look-back warps run the batched decoupled look-back next to the scatter.
+//   * the look-back warps run a TWO-LEVEL decoupled look-back next to the scatter: 16-bit tile counts
+//     inside groups of 8 tiles, 32-bit group words (count, later inclusive prefix) across groups.
 // PACK (u32 keys + 4-byte values): key and value cross shared memory as ONE 8-byte word.
 // (A persistent, warp-specialised variant with the next tile's keys loaded during the write-out
 //  was tried; ptxas 12.9 spills the key/rank registers in every loop form tried, which costs more
@@ -625,6 +628,9 @@ template <class U, class VT, class C, class S> struct LateSmem {
   G gbase[RADIX];           // global position of tile-rank r of digit d = gbase[d] + r (mod 2^bits)
   uint32_t wtot[RADIX / WARP];
   long long tile;
+#ifdef RB200_LB_TRACE
+  unsigned long long t_compute, t_lb;  // arrival times at the barrier before the write-out
+#endif
   alignas(16) U keys[S::TILE];
   typename std::conditional<HAS_VALUES, VT, char>::type vals[HAS_VALUES ? S::TILE : 1];  // PACK: keys..vals is one uint2[TILE]
 };
@@ -653,6 +659,12 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
   const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
   const bool compute = tid < BLOCK;
   if (tid == 0) s.tile = (long long)atomicAdd(ticket, 1u);
+#ifdef RB200_LB_TRACE
+  if (tid == 0) {
+    s.t_compute = 0;
+    s.t_lb = 0;
+  }
+#endif
   for (int i = tid; i < NW * RADIX; i += S::THREADS) (&s.cnt[0][0])[i] = 0;
   __syncthreads();
   const long long tile = s.tile;
@@ -794,108 +806,167 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
       }
     }
   } else {
-    // look-back warps: lane owns D consecutive digits.  Per round trip: the 16-bit counts of B
-    // predecessors (one 8-byte load = 4 digits of one tile) plus the finished prefixes of the
-    // predecessors at checkpoints CK0 and CK1 of the batch; the walk ends at the first checkpoint
-    // whose prefix is there (or at tile 0), adding the counts of the tiles in between.
+    // look-back warps: lane owns D consecutive digits.  Two-level look-back: tiles form groups of 8;
+    // the LAST tile of a group publishes, per digit, first the group's count (LOCAL flag: the sum of
+    // its seven in-group predecessors' counts, which it reads anyway, plus its own) and later the
+    // inclusive prefix through the group's end (GLOBAL flag) into lookback[group][digit].  A tile
+    // then needs (a) the 16-bit counts of its <= 7 in-group predecessors and (b) group words walking
+    // back until a GLOBAL one -- both fetched in the SAME round trip -- instead of walking ~40 tiles
+    // back 8 at a time: the compute warps used to wait ~6.8 K cycles per tile for five to six look-back
+    // round trips (measured with -DRB200_LB_TRACE: the look-back arrived last at the barrier below in
+    // 100 % of the tiles).
     constexpr int NQ = RADIX / (LBT * 4);  // groups of 4 digits per lane: 1 (two look-back warps) or 2 (one)
     constexpr int D = 4 * NQ;
+    constexpr int GT = S::LB_GROUP;        // tiles per group
+    constexpr int NG = S::LB_BATCH;        // group words in flight per lane
     const int q = (tid - BLOCK) * D;
-    C prev[D] = {};
-    if (tile != 0) {
-      constexpr int B = (sizeof(C) == 4 ? 2 : 1) * S::LB_BATCH / NQ;
-      constexpr int CK0 = B / 2 - 1, CK1 = B - 1;
-      long long p = tile - 1;
+    const long long grp = tile / GT;
+    const int k = (int)(tile - grp * GT);  // in-group predecessors: tile-1 .. tile-k
+    C prev[D] = {};                        // counts of everything before this tile
+    C ingroup[D] = {};                     // counts of the in-group predecessors
+    {
+      unsigned pending = (1u << k) - 1u;   // bit b: in-group predecessor tile-1-b not yet added
+      bool gdone[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) gdone[c] = (grp == 0);
+      bool groups_done = (grp == 0);
+      bool owner_published = false;
+      long long gh = grp - 1;              // next group word to consume
 #ifdef RB200_LB_TRACE
       unsigned lb_rounds = 0;
 #endif
-      while (true) {
+      unsigned spins = 0;
+      while (pending != 0u || !groups_done) {
 #ifdef RB200_LB_TRACE
         ++lb_rounds;
 #endif
-        uint2 v[B][NQ];
-        Quad<C> g0[NQ], g1[NQ];
+        if (++spins > (1u << 24)) __trap();  // a predecessor never published: fail instead of hanging the device
+        // ---- issue every load of this round
+        uint2 v[GT - 1][NQ];
+        Quad<C> gw[NG][NQ];
 #pragma unroll
-        for (int b = 0; b < B; ++b)
+        for (int b = 0; b < GT - 1; ++b)
 #pragma unroll
-          for (int k = 0; k < NQ; ++k) {
-            v[b][k] = make_uint2(0u, 0u);
-            if (p - b >= 0) {
-              const unsigned long long w64 = ld_relaxed_u64(reinterpret_cast<const uint64_t*>(local16 + (p - b) * RADIX + q + 4 * k));
-              v[b][k] = make_uint2((uint32_t)w64, (uint32_t)(w64 >> 32));
+          for (int kq = 0; kq < NQ; ++kq) {
+            v[b][kq] = make_uint2(0u, 0u);
+            if (pending & (1u << b)) {
+              const unsigned long long w64 = ld_relaxed_u64(reinterpret_cast<const uint64_t*>(local16 + (tile - 1 - b) * RADIX + q + 4 * kq));
+              v[b][kq] = make_uint2((uint32_t)w64, (uint32_t)(w64 >> 32));
             }
           }
+        if (!groups_done) {
 #pragma unroll
-        for (int k = 0; k < NQ; ++k) {
-          g0[k] = Quad<C>{{0, 0, 0, 0}};
-          g1[k] = Quad<C>{{0, 0, 0, 0}};
-          if (p - CK0 >= 0) g0[k] = ld_quad(lookback + (p - CK0) * RADIX + q + 4 * k);
-          if (p - CK1 >= 0) g1[k] = ld_quad(lookback + (p - CK1) * RADIX + q + 4 * k);
+          for (int b = 0; b < NG; ++b)
+#pragma unroll
+            for (int kq = 0; kq < NQ; ++kq) {
+              gw[b][kq] = Quad<C>{{F::GLOBAL, F::GLOBAL, F::GLOBAL, F::GLOBAL}};  // before the first group: zero, final
+              if (gh - b >= 0) gw[b][kq] = ld_quad(lookback + (gh - b) * RADIX + q + 4 * kq);
+            }
         }
-        int consumed = 0;
-        bool all_done = false;
+        // ---- in-group counts (any order: a sum)
+        bool progress = false;
 #pragma unroll
-        for (int b = 0; b < B; ++b) {
-          if (all_done) break;
-          if (p - b < 0) {  // walked past tile 0: everything before is counted
-            all_done = true;
-            break;
-          }
-          if (b == CK0 || b == CK1) {
-            bool ready = true;
+        for (int b = 0; b < GT - 1; ++b) {
+          if (pending & (1u << b)) {
+            uint32_t e[D];
 #pragma unroll
-            for (int c = 0; c < D; ++c) ready = ready && (((b == CK0 ? g0 : g1)[c >> 2].v[c & 3] & F::GLOBAL) != 0);
-            if (__all_sync(FULL_MASK, ready)) {
+            for (int kq = 0; kq < NQ; ++kq) {
+              e[4 * kq + 0] = v[b][kq].x & 0xffffu;
+              e[4 * kq + 1] = v[b][kq].x >> 16;
+              e[4 * kq + 2] = v[b][kq].y & 0xffffu;
+              e[4 * kq + 3] = v[b][kq].y >> 16;
+            }
+            bool ok = true;
 #pragma unroll
-              for (int c = 0; c < D; ++c) prev[c] += (b == CK0 ? g0 : g1)[c >> 2].v[c & 3] & F::MASK;
-              all_done = true;
-              break;
+            for (int c = 0; c < D; ++c) ok = ok && (e[c] != 0);
+            if (__all_sync(FULL_MASK, ok)) {
+#pragma unroll
+              for (int c = 0; c < D; ++c) ingroup[c] += (C)(e[c] - 1);
+              pending &= ~(1u << b);
+              progress = true;
             }
           }
-          uint32_t e[D];
-#pragma unroll
-          for (int k = 0; k < NQ; ++k) {
-            e[4 * k + 0] = v[b][k].x & 0xffffu;
-            e[4 * k + 1] = v[b][k].x >> 16;
-            e[4 * k + 2] = v[b][k].y & 0xffffu;
-            e[4 * k + 3] = v[b][k].y >> 16;
-          }
-          bool ok = true;
-#pragma unroll
-          for (int c = 0; c < D; ++c) ok = ok && (e[c] != 0);
-          if (!__all_sync(FULL_MASK, ok)) break;  // this predecessor has not published its counts yet: re-poll from here
-#pragma unroll
-          for (int c = 0; c < D; ++c) prev[c] += (C)(e[c] - 1);
-          ++consumed;
         }
-        if (all_done) {
-#ifdef RB200_LB_TRACE
-          if (tid == BLOCK) {  // ticket[8..11]: rounds, depth, max depth, tiles
-            atomicAdd(ticket + 8, lb_rounds);
-            atomicAdd(ticket + 9, (unsigned)(tile - 1 - p + consumed));
-            atomicMax(ticket + 10, (unsigned)(tile - 1 - p + consumed));
-            atomicAdd(ticket + 11, 1u);
+        // the group's last tile: the group's count, as soon as its seven predecessors are in
+        if (k == GT - 1 && pending == 0u && !owner_published) {
+#pragma unroll
+          for (int kq = 0; kq < NQ; ++kq) {
+            Quad<C> g;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) g.v[c] = (C)(ingroup[4 * kq + c] + s.count[q + 4 * kq + c]) | F::LOCAL;
+            st_quad(lookback + grp * RADIX + q + 4 * kq, g);
           }
-#endif
-          break;
+          owner_published = true;
         }
-        p -= consumed;
-        if (consumed < B) __nanosleep(consumed == 0 ? S::LB_SLEEP : S::LB_SLEEP / 4);  // leave the issue slots to the scatter
+        // ---- group words, nearest first, until every digit has met a GLOBAL one
+        if (!groups_done) {
+          int consumed = 0;
+#pragma unroll
+          for (int b = 0; b < NG; ++b) {
+            if (groups_done) break;
+            bool ok = true;
+#pragma unroll
+            for (int c = 0; c < D; ++c) ok = ok && (gdone[c] || (gw[b][c >> 2].v[c & 3] & ~F::MASK) != 0);
+            if (!__all_sync(FULL_MASK, ok)) break;  // this group has not published yet: re-poll from here
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+              if (!gdone[c]) {
+                prev[c] += gw[b][c >> 2].v[c & 3] & F::MASK;
+                if (gw[b][c >> 2].v[c & 3] & F::GLOBAL) gdone[c] = true;
+              }
+            }
+            ++consumed;
+            bool mine = true;
+#pragma unroll
+            for (int c = 0; c < D; ++c) mine = mine && gdone[c];
+            groups_done = __all_sync(FULL_MASK, mine);
+          }
+          gh -= consumed;
+          progress = progress || consumed > 0;
+        }
+        if (!progress) __nanosleep(S::LB_SLEEP / 4);  // leave the issue slots to the scatter
       }
-    }
-    {
 #pragma unroll
-      for (int k = 0; k < NQ; ++k) {
+      for (int c = 0; c < D; ++c) prev[c] += ingroup[c];
+#ifdef RB200_LB_TRACE
+      if (tid == BLOCK) {  // this pass's ticket word + 8 / 16 / 24: look-back rounds, depth (tiles + groups read), tiles
+        atomicAdd(ticket + 8, lb_rounds);
+        atomicAdd(ticket + 16, (unsigned)(k + (grp - 1 - gh)));
+        atomicAdd(ticket + 24, 1u);
+      }
+#endif
+    }
+    if (k == GT - 1) {  // the inclusive prefix through the group's end, for the groups behind
+#pragma unroll
+      for (int kq = 0; kq < NQ; ++kq) {
         Quad<C> g;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) g.v[c] = (C)(prev[4 * k + c] + s.count[q + 4 * k + c]) | F::GLOBAL;
-        st_quad(lookback + tile * RADIX + q + 4 * k, g);
+        for (int c = 0; c < 4; ++c) g.v[c] = (C)(prev[4 * kq + c] + s.count[q + 4 * kq + c]) | F::GLOBAL;
+        st_quad(lookback + grp * RADIX + q + 4 * kq, g);
       }
     }
 #pragma unroll
     for (int c = 0; c < D; ++c) s.gbase[q + c] = (G)(bin_base[q + c] + (unsigned long long)prev[c]) - (G)s.texcl[q + c];
   }
+#ifdef RB200_LB_TRACE
+  // who arrives last at this barrier: the scatter or the look-back?  ticket + 32: tiles where the look-back was
+  // last, + 40: by how much in total (units of 64 cycles), + 48: the reverse
+  if (l == 0) {
+    if (compute) atomicMax(&s.t_compute, (unsigned long long)clock64());
+    else atomicMax(&s.t_lb, (unsigned long long)clock64());
+  }
+#endif
   __syncthreads();
+#ifdef RB200_LB_TRACE
+  if (tid == 0) {
+    if (s.t_lb > s.t_compute) {
+      atomicAdd(ticket + 32, 1u);
+      atomicAdd(ticket + 40, (unsigned)((s.t_lb - s.t_compute) >> 6));
+    } else {
+      atomicAdd(ticket + 48, (unsigned)((s.t_compute - s.t_lb) >> 6));
+    }
+  }
+#endif
 
   // ---- phase D: run-coalesced write-out ------------------------------------------------------------
   if (compute) {
@@ -947,7 +1018,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 template <class U, class VT> struct Tuning {
   static constexpr int VB = std::is_same<VT, NoValue>::value ? 0 : (int)sizeof(VT);
   static constexpr int ITEMS = sizeof(U) == 4 ? (VB <= 4 ? 30 : 20) : (VB == 0 ? 18 : (VB == 4 ? 16 : 14));
-  using shape = SweepShape<256, ITEMS, 3, 3, false, 300, 2, 4>;
+  using shape = SweepShape<256, ITEMS, 3, 3, false, 300, 2, 2>;
 };
 
 template <class U, class VT, class S = typename Tuning<U, VT>::shape> inline long long num_tiles(long long n)
@@ -1094,7 +1165,7 @@ template <class U, class VT> struct PartitionTuning {
   // the three digit evaluations per key inside the register budget
   static constexpr int VB = std::is_same<VT, NoValue>::value ? 0 : (int)sizeof(VT);
   static constexpr int ITEMS = sizeof(U) == 4 ? (VB <= 4 ? 24 : 16) : (VB == 0 ? 14 : 12);
-  using shape = SweepShape<256, ITEMS, 3, 3, false, 300, 2, 4>;
+  using shape = SweepShape<256, ITEMS, 3, 3, false, 300, 2, 2>;
 };
 
 // workspace: same layout as sort's ([ghist 256 u64 x NPASS][bin_base ...][tickets][lookback]); only pass 0 is used
