@@ -8,6 +8,7 @@
 //     RAJA::b200_multi_reduce               (MultiReduceSum/Min/Max/BitOr/BitAnd: run-time indexed bins)
 //     RAJA::b200_atomic                     (atomicAdd & friends)
 //     RAJA::b200_synchronize
+//     RAJA::b200_launch_t<Async>            (RAJA::launch, with or without expt::Reduce params)
 //     RAJA::b200::{device,device_zeroed,pinned}_mempool_type
 //
 // usable with RAJA::forall (with or without RAJA::expt::Reduce / ReduceLoc / Name params),
@@ -76,5 +77,6 @@
 #include "RAJA_b200/forall.hpp"
 #include "RAJA_b200/reduce.hpp"
 #include "RAJA_b200/multi_reduce.hpp"
+#include "RAJA_b200/launch.hpp"
 
 #endif  // RAJA_B200_RAJA_HPP

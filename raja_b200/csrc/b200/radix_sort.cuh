@@ -617,12 +617,23 @@ template <class U, class VT> struct PeerSplitDigit : SplitDigit<U> {
 //  was tried; ptxas 12.9 spills the key/rank registers in every loop form tried, which costs more
 //  LSU wavefronts than the variant saves -- see DESIGN.md.)
 // ---------------------------------------------------------------------------
+// look-back words of one pass: the early-count kernel keeps one C word per (tile, digit); the late-count
+// kernel one C word per (group of LB_GROUP tiles, digit) + one u16 per (tile, digit)
+template <class S> B200_HD long long lookback_groups(long long ntiles)
+{
+  return S::MATCH >= 3 ? (ntiles + S::LB_GROUP - 1) / S::LB_GROUP : ntiles;
+}
+template <class S> inline size_t lookback_bytes(long long ntiles, size_t cbytes)
+{
+  return (size_t)lookback_groups<S>(ntiles) * RADIX * cbytes + (size_t)ntiles * RADIX * 2;
+}
+
 template <class U, class VT, class C, class S> struct LateSmem {
   static constexpr int NW = S::BLOCK / WARP;
   static constexpr bool HAS_VALUES = !std::is_same<VT, NoValue>::value;
   static constexpr bool PACK = S::PACK && HAS_VALUES && sizeof(U) == 4 && sizeof(VT) == 4;
   using G = typename std::conditional<sizeof(C) == 4, uint32_t, unsigned long long>::type;
-  uint32_t cnt[NW][RADIX];  // running rank of (warp, digit) -> total -> first tile rank
+  uint16_t cnt[NW][RADIX];  // running rank of (warp, digit) -> total -> first tile rank (< TILE < 65535; 16 bits: 4 KB more for keys)
   uint16_t count[RADIX];    // digit counts of this tile (TILE < 65536)
   uint32_t texcl[RADIX];    // first rank of each digit inside this tile
   G gbase[RADIX];           // global position of tile-rank r of digit d = gbase[d] + r (mod 2^bits)
@@ -641,7 +652,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
                      const VT* __restrict__ vals_in, VT* __restrict__ vals_out,
                      const long long n,
                      const unsigned long long* __restrict__ bin_base,  // [256] of this pass
-                     C* lookback,                                      // [ntiles][256] inclusive prefixes, then [ntiles][256] u16 tile counts; zero on entry
+                     C* lookback,                                      // [ngroups][256] group words, then [ntiles][256] u16 tile counts; zero on entry
                      unsigned* ticket,                                 // zero on entry
                      const DigitFn digit)
 {
@@ -665,7 +676,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
     s.t_lb = 0;
   }
 #endif
-  for (int i = tid; i < NW * RADIX; i += S::THREADS) (&s.cnt[0][0])[i] = 0;
+  for (int i = tid; i < NW * RADIX / 2; i += S::THREADS) reinterpret_cast<uint32_t*>(&s.cnt[0][0])[i] = 0;
   __syncthreads();
   const long long tile = s.tile;
   const long long tile_base = tile * TILE;
@@ -677,7 +688,8 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
   // its own look-back is done.  16-bit counts let a look-back lane keep 16 predecessors in flight in
   // the registers 8 took before: the rate at which finished prefixes propagate from tile to tile
   // (predecessors consumed per L2 round trip) is what bounds the pass, not HBM or the LSU.
-  uint16_t* const local16 = reinterpret_cast<uint16_t*>(lookback + ((n + TILE - 1) / TILE) * RADIX);
+  // Layout of one pass's look-back region: [groups][256] C group words, then [tiles][256] u16 counts.
+  uint16_t* const local16 = reinterpret_cast<uint16_t*>(lookback + lookback_groups<S>((n + TILE - 1) / TILE) * RADIX);
 
   U key[ITEMS];            // warp-striped: item (j, l) is tile item wofs + j*32 + l
   uint32_t rp[ITEMS / 2];  // two 16-bit ranks per register: warp-local first, tile ranks later
@@ -703,7 +715,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
     }
   }
   if (compute) {
-    uint32_t* const wc = s.cnt[w];
+    uint16_t* const wc = s.cnt[w];
     const unsigned lt = lanemask_lt();
     auto rank_rows = [&](auto full_c) {
       constexpr bool FULL = decltype(full_c)::value;
@@ -717,7 +729,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
         const unsigned below = peers & lt;
         const uint32_t r = c + __popc(below);
         __syncwarp();
-        if (valid && below == 0) wc[d] = c + __popc(peers);
+        if (valid && below == 0) wc[d] = (uint16_t)(c + __popc(peers));
         __syncwarp();
         if (j & 1) rp[j >> 1] |= r << 16;
         else rp[j >> 1] = r;
@@ -752,7 +764,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 #pragma unroll
     for (int i = 0; i < NW; ++i) {  // re-read rather than hold NW counts across the scan (register budget)
       const uint32_t c = s.cnt[i][tid];
-      s.cnt[i][tid] = run;
+      s.cnt[i][tid] = (uint16_t)run;
       run += c;
     }
   }
@@ -760,7 +772,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 
   // ---- phase C: scatter into shared memory in tile-rank order | look-back -----------------------
   if (compute) {
-    const uint32_t* const wc = s.cnt[w];
+    const uint16_t* const wc = s.cnt[w];
     uint2* const pairs = reinterpret_cast<uint2*>(s.keys);
     (void)pairs;
     auto scatter = [&](auto full_c) {
@@ -1017,7 +1029,7 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 // prefetched to L2; ITEMS is what the 64-register budget of that occupancy holds per key/value width.
 template <class U, class VT> struct Tuning {
   static constexpr int VB = std::is_same<VT, NoValue>::value ? 0 : (int)sizeof(VT);
-  static constexpr int ITEMS = sizeof(U) == 4 ? (VB <= 4 ? 30 : 20) : (VB == 0 ? 18 : (VB == 4 ? 16 : 14));
+  static constexpr int ITEMS = sizeof(U) == 4 ? (VB <= 4 ? 32 : 20) : (VB == 0 ? 18 : (VB == 4 ? 16 : 14));
   using shape = SweepShape<256, ITEMS, 3, 3, false, 300, 2, 2>;
 };
 
@@ -1026,13 +1038,14 @@ template <class U, class VT, class S = typename Tuning<U, VT>::shape> inline lon
   return (n + S::TILE - 1) / S::TILE;
 }
 
-// workspace layout: [ghist NPASS*256 u64][bin_base NPASS*256 u64][tickets NPASS u32, padded][lookback ntiles*256*C]
+// workspace layout: [ghist NPASS*256 u64][bin_base NPASS*256 u64][tickets NPASS u32, padded][NPASS look-back regions]
+// (one region per pass, so that ONE memset up front clears the whole sort)
 template <class U, class VT, class S = typename Tuning<U, VT>::shape> inline size_t workspace_bytes(long long n)
 {
   constexpr int NPASS = sizeof(U);
   size_t header = (size_t)NPASS * RADIX * 8 * 2 + 256;
   size_t cbytes = (n < (1ll << 30)) ? 4 : 8;
-  return header + (size_t)num_tiles<U, VT, S>(n) * RADIX * (cbytes + 2);  // inclusive prefixes + 16-bit tile counts
+  return header + NPASS * lookback_bytes<S>(num_tiles<U, VT, S>(n), cbytes);
 }
 
 // opt-in to > 48 KB of dynamic shared memory, once per kernel (keyed on the kernel itself:
@@ -1096,11 +1109,10 @@ inline cudaError_t sort(cudaStream_t stream, U* keys, U* keys_alt, VT* vals, VT*
   unsigned long long* ghist = (unsigned long long*)workspace;
   unsigned long long* bin_base = ghist + NPASS * RADIX;
   unsigned* tickets = (unsigned*)(bin_base + NPASS * RADIX);
-  void* lookback = (char*)workspace + header;
   const bool small = n < (1ll << 30);
-  const size_t lb_bytes = (size_t)num_tiles<U, VT, S>(n) * RADIX * ((small ? 4 : 8) + 2);
+  const size_t lb_bytes = lookback_bytes<S>(num_tiles<U, VT, S>(n), small ? 4 : 8);
 
-  cudaError_t e = cudaMemsetAsync(workspace, 0, header + lb_bytes, stream);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, header + NPASS * lb_bytes, stream);
   if (e != cudaSuccess) return e;
   {
     using H = HistShape<U>;
@@ -1122,10 +1134,7 @@ inline cudaError_t sort(cudaStream_t stream, U* keys, U* keys_alt, VT* vals, VT*
     U* kout = (p & 1) ? keys : keys_alt;
     const VT* vin = (p & 1) ? vals_alt : vals;
     VT* vout = (p & 1) ? vals : vals_alt;
-    if (p > 0) {
-      e = cudaMemsetAsync(lookback, 0, lb_bytes, stream);
-      if (e != cudaSuccess) return e;
-    }
+    void* lookback = (char*)workspace + header + p * lb_bytes;
     if (small)
       e = launch_pass<U, VT, uint32_t, S>(stream, kin, kout, vin, vout, n, bin_base + p * RADIX, lookback, tickets + p, p * RADIX_BITS, order);
     else
@@ -1183,7 +1192,7 @@ inline cudaError_t bucket_counts(cudaStream_t stream, const U* keys_in, long lon
   unsigned long long* ghist = (unsigned long long*)workspace;
   const bool small = n < (1ll << 30);
   const long long ntiles = num_tiles<U, VT, S>(n > 0 ? n : 1);
-  const size_t lb_bytes = (size_t)ntiles * RADIX * ((small ? 4 : 8) + 2);
+  const size_t lb_bytes = lookback_bytes<S>(ntiles, small ? 4 : 8);
   cudaError_t e = cudaMemsetAsync(workspace, 0, header + lb_bytes, stream);
   if (e != cudaSuccess) return e;
   if (n > 0) {

@@ -107,8 +107,12 @@ template <class T> struct TileState<T, false> {
 //   SLOTS  shared-memory tile slots; LAG = how many outgoing copies may still be reading
 //          their slot when the next load is issued.  Tile i+2 is reduced while tile i is
 //          scanned, so SLOTS >= 4 + LAG; loads run SLOTS-1-LAG tiles ahead of the scan.
-template <int BLOCK_, int VPT_, int ROWS_, int SLOTS_ = 4, int LAG_ = 0> struct Shape {
+//   SERIAL the reduce step leaves every thread's total in shared memory and the scan step is ONE
+//          running chain per thread seeded with the thread's exclusive prefix: 2 combines per element
+//          (reduce + scan) instead of 3.5 -- for operators whose combine is expensive (FP64 adds)
+template <int BLOCK_, int VPT_, int ROWS_, int SLOTS_ = 4, int LAG_ = 0, bool SERIAL_ = false> struct Shape {
   static constexpr int BLOCK = BLOCK_, VPT = VPT_, ROWS = ROWS_, SLOTS = SLOTS_, LAG = LAG_;
+  static constexpr bool SERIAL = SERIAL_;
   static constexpr int THREADS = BLOCK + WARP;
   static constexpr int AHEAD = SLOTS - 1 - LAG;
   static_assert(BLOCK % WARP == 0 && BLOCK + WARP <= 1024, "");
@@ -126,7 +130,8 @@ template <class T, class S> struct Layout {
   static constexpr size_t OFF_WARP = OFF_BAR + 8 * S::SLOTS;
   static constexpr size_t OFF_PREFIX = OFF_WARP + 3 * 8 * 32;
   static constexpr size_t OFF_VID = OFF_PREFIX + 16;
-  static constexpr size_t SMEM_BYTES = OFF_VID + 8;
+  static constexpr size_t OFF_THREAD = OFF_VID + 8;  // SERIAL: thread totals of tile i at [(i % 3) * BLOCK + tid]
+  static constexpr size_t SMEM_BYTES = OFF_THREAD + (S::SERIAL ? 3 * S::BLOCK * sizeof(T) : 0);
 };
 
 enum : int { F_BULK_IN = 1, F_BULK_OUT = 2,  // pointer is 16-byte aligned: bulk copies allowed
@@ -150,6 +155,8 @@ scan_kernel(const T* in, T* out, const long long n, const T init, const T* carry
   T* const s_warp = reinterpret_cast<T*>(smem + L::OFF_WARP);      // warp totals of tile i at [(i % 3) * 32 + warp]
   T* const s_prefix = reinterpret_cast<T*>(smem + L::OFF_PREFIX);  // exclusive prefix of tile i at [i & 1]
   unsigned* const s_vid = reinterpret_cast<unsigned*>(smem + L::OFF_VID);
+  T* const s_thread = reinterpret_cast<T*>(smem + L::OFF_THREAD);
+  (void)s_thread;
 
   const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
   const bool is_lb = (w == NW);           // the look-back warp; its lane 0 also owns every bulk copy
@@ -219,6 +226,7 @@ scan_kernel(const T* in, T* out, const long long n, const T init, const T* carry
 #pragma unroll
       for (int v = 0; v + st < VPT; v += 2 * st) pv[v] = op(pv[v], pv[v + st]);
     T acc = pv[0];
+    if constexpr (S::SERIAL) s_thread[(i % 3) * BLOCK + tid] = acc;
     // ordered fold across lanes (lower lane on the left)
 #pragma unroll
     for (int d = 1; d < WARP; d <<= 1) {
@@ -326,44 +334,78 @@ scan_kernel(const T* in, T* out, const long long n, const T init, const T* carry
       // ---- scan tile i with its prefix, write it back into the slot ---------------------------
       // inclusive scan inside each 16-byte vector (independent chains), then a serial scan over the
       // VPT vector totals only: dependent depth (V-1) + (VPT-1) instead of ITEMS-1
-      T x[ITEMS];   // x[v*V + j]: inclusive scan of vector v up to element j
-      T vpre[VPT];  // vpre[v]: total of the vectors before v (v >= 1)
+      if constexpr (S::SERIAL) {
+        T sc = s_thread[(i % 3) * BLOCK + tid];  // own total, left there by reduce_and_publish(i) (same thread)
 #pragma unroll
-      for (int v = 0; v < VPT; ++v) {
-        VT t = reinterpret_cast<const VT*>(buf)[tid * VPT + v];
-        x[v * V] = t.e[0];
-#pragma unroll
-        for (int j = 1; j < V; ++j) x[v * V + j] = op(x[v * V + j - 1], t.e[j]);
-      }
-      vpre[0] = ident;
-      if (VPT > 1) vpre[1] = x[V - 1];
-#pragma unroll
-      for (int v = 2; v < VPT; ++v) vpre[v] = op(vpre[v - 1], x[(v - 1) * V + V - 1]);
-      T sc = (VPT > 1) ? op(vpre[VPT - 1], x[ITEMS - 1]) : x[ITEMS - 1];
-#pragma unroll
-      for (int d = 1; d < WARP; d <<= 1) {
-        T o = shfl_up(sc, d);
-        if (l >= d) sc = op(o, sc);
-      }
-      T lane_excl = shfl_up(sc, 1);
-      if (l == 0) lane_excl = ident;
-      T wprefix = ident;
-#pragma unroll
-      for (int k = 0; k < NW; ++k) {
-        T t = s_warp[(i % 3) * 32 + k];
-        if (k < w) wprefix = op(wprefix, t);
-      }
-      const T pre = op(op(s_prefix[i & 1], wprefix), lane_excl);
-#pragma unroll
-      for (int v = 0; v < VPT; ++v) {
-        const T pre_v = (v == 0) ? pre : op(pre, vpre[v]);  // everything before this vector
-        VT t;
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-          if (Inclusive) t.e[j] = op(pre_v, x[v * V + j]);
-          else t.e[j] = (j == 0) ? pre_v : op(pre_v, x[v * V + j - 1]);
+        for (int d = 1; d < WARP; d <<= 1) {
+          T o = shfl_up(sc, d);
+          if (l >= d) sc = op(o, sc);
         }
-        reinterpret_cast<VT*>(buf)[tid * VPT + v] = t;
+        T lane_excl = shfl_up(sc, 1);
+        if (l == 0) lane_excl = ident;
+        T wprefix = ident;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+          T t = s_warp[(i % 3) * 32 + k];
+          if (k < w) wprefix = op(wprefix, t);
+        }
+        T run = op(op(s_prefix[i & 1], wprefix), lane_excl);
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+          VT t = reinterpret_cast<const VT*>(buf)[tid * VPT + v];
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            if (Inclusive) {
+              run = op(run, t.e[j]);
+              t.e[j] = run;
+            } else {
+              const T e = t.e[j];
+              t.e[j] = run;
+              run = op(run, e);
+            }
+          }
+          reinterpret_cast<VT*>(buf)[tid * VPT + v] = t;
+        }
+      } else {
+        T x[ITEMS];   // x[v*V + j]: inclusive scan of vector v up to element j
+        T vpre[VPT];  // vpre[v]: total of the vectors before v (v >= 1)
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+          VT t = reinterpret_cast<const VT*>(buf)[tid * VPT + v];
+          x[v * V] = t.e[0];
+#pragma unroll
+          for (int j = 1; j < V; ++j) x[v * V + j] = op(x[v * V + j - 1], t.e[j]);
+        }
+        vpre[0] = ident;
+        if (VPT > 1) vpre[1] = x[V - 1];
+#pragma unroll
+        for (int v = 2; v < VPT; ++v) vpre[v] = op(vpre[v - 1], x[(v - 1) * V + V - 1]);
+        T sc = (VPT > 1) ? op(vpre[VPT - 1], x[ITEMS - 1]) : x[ITEMS - 1];
+#pragma unroll
+        for (int d = 1; d < WARP; d <<= 1) {
+          T o = shfl_up(sc, d);
+          if (l >= d) sc = op(o, sc);
+        }
+        T lane_excl = shfl_up(sc, 1);
+        if (l == 0) lane_excl = ident;
+        T wprefix = ident;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+          T t = s_warp[(i % 3) * 32 + k];
+          if (k < w) wprefix = op(wprefix, t);
+        }
+        const T pre = op(op(s_prefix[i & 1], wprefix), lane_excl);
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+          const T pre_v = (v == 0) ? pre : op(pre, vpre[v]);  // everything before this vector
+          VT t;
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            if (Inclusive) t.e[j] = op(pre_v, x[v * V + j]);
+            else t.e[j] = (j == 0) ? pre_v : op(pre_v, x[v * V + j - 1]);
+          }
+          reinterpret_cast<VT*>(buf)[tid * VPT + v] = t;
+        }
       }
       if (bulk_out) {
         fence_proxy_async();  // generic-proxy writes above -> async-proxy read by the bulk store
@@ -392,11 +434,14 @@ template <class T> struct Tuning {
   // 6.32 TB/s (int64) at N = 2^28, 96 % of a device memcpy (profiles/r01_scan_tuning.txt).
   using shape = Shape<384, 7, 10, 5, 0>;
 };
-// Floating-point 8-byte scans are bound by the per-round latency of the dependent FP64 adds (DADD
-// 8.3 cycles against 2-3 for IADD: profiles/r01_scan_fp64_notes.txt), not by bandwidth, so they
-// take the largest tile that still leaves four slots: 54 KB, 5.27 TB/s against 4.49 TB/s.
+// FP64 scans are bound by the NUMBER of DADDs issued, not by their latency or by bandwidth: the
+// ILP-friendly scan step above costs 2.5 combines per element on top of the reduce step's 1, and
+// the same kernel with an integer add on the bit patterns runs at the int64 rate.  SERIAL (thread
+// totals kept in shared memory, one running chain per thread: 2 combines per element) with the
+// largest tile that leaves four slots: 5.89 TB/s = 90 % of the measured peak, against 5.27 TB/s
+// for the same tile without SERIAL and 4.49 TB/s for the integer shape (profiles/r01_scan_tuning_v4.txt).
 template <> struct Tuning<double> {
-  using shape = Shape<384, 9, 10, 4, 0>;
+  using shape = Shape<384, 9, 10, 4, 0, true>;
 };
 
 template <class T, class Op, bool Inclusive, class S>

@@ -56,7 +56,7 @@ template <class T, class S> void run_shape(const char* tname, const T* in, T* ou
   CK(cudaMemcpy(&h, bad, 8, cudaMemcpyDeviceToHost));
   int occ = 0;
   scan::configure<T, Plus<T>, true, S>(&occ);
-  printf("%-4s BLOCK=%4d VPT=%2d ROWS=%2d SLOTS=%d LAG=%d tile=%6.1fKB smem=%6.1fKB occ=%d : %8.4f ms %8.1f GB/s %s\n", tname, S::BLOCK, S::VPT, S::ROWS, S::SLOTS, S::LAG,
+  printf("%-4s BLOCK=%4d VPT=%2d ROWS=%2d SLOTS=%d LAG=%d SERIAL=%d tile=%6.1fKB smem=%6.1fKB occ=%d : %8.4f ms %8.1f GB/s %s\n", tname, S::BLOCK, S::VPT, S::ROWS, S::SLOTS, S::LAG, (int)S::SERIAL,
          scan::Layout<T, S>::TILE_BYTES / 1024.0, scan::Layout<T, S>::SMEM_BYTES / 1024.0, occ, ms, 2.0 * n * sizeof(T) / ms / 1e6, h ? "MISMATCH" : "ok");
   fflush(stdout);
 }
@@ -82,6 +82,8 @@ template <class T> void run_type(const char* tname, long long n)
   run_shape<T, scan::Shape<384, 7, 10, 5, 0>>(tname, in, out, ref, n, ws, bad);  // 210 KB
   run_shape<T, scan::Shape<384, 7, 10, 5, 1>>(tname, in, out, ref, n, ws, bad);
   run_shape<T, scan::Shape<384, 9, 10>>(tname, in, out, ref, n, ws, bad);        // 216 KB
+  run_shape<T, scan::Shape<384, 9, 10, 4, 0, true>>(tname, in, out, ref, n, ws, bad);  // + thread totals: 226 KB
+  run_shape<T, scan::Shape<384, 7, 10, 5, 0, true>>(tname, in, out, ref, n, ws, bad);  // 220 KB
   run_shape<T, scan::Shape<512, 5, 10>>(tname, in, out, ref, n, ws, bad);        // 160 KB
   run_shape<T, scan::Shape<512, 5, 10, 5, 0>>(tname, in, out, ref, n, ws, bad);  // 200 KB
   run_shape<T, scan::Shape<512, 5, 10, 5, 1>>(tname, in, out, ref, n, ws, bad);

@@ -127,14 +127,11 @@ int main(int argc, char** argv)
     cudaFree(tmp);
   }
 #if TK == 0
-  run_shape<rsort::SweepShape<384, 24, 2, 2>>(b);
-  run_shape<rsort::SweepShape<256, 30, 3, 3, false, 300>>(b);
-  run_shape<rsort::SweepShape<256, 30, 3, 3, false, 300, 2, 4>>(b);
-  run_shape<rsort::SweepShape<256, 30, 3, 3, false, 300, 2, 12>>(b);
-  run_shape<rsort::SweepShape<256, 30, 3, 3, false, 300, 1, 8>>(b);
-  run_shape<rsort::SweepShape<256, 32, 3, 3, false, 300, 1, 8>>(b);
-  run_shape<rsort::SweepShape<384, 24, 2, 3, false, 200>>(b);
-  run_shape<rsort::SweepShape<256, 24, 3, 3, false, 400>>(b);
+  run_shape<rsort::SweepShape<256, 32, 3, 3, false, 300, 2, 2>>(b);
+  run_shape<rsort::SweepShape<256, 32, 3, 3, false, 300, 1, 2>>(b);
+  run_shape<rsort::SweepShape<256, 34, 3, 3, false, 300, 1, 2>>(b);
+  run_shape<rsort::SweepShape<256, 32, 3, 3, false, 300, 1, 1>>(b);
+  run_shape<rsort::SweepShape<256, 34, 3, 3, false, 300, 1, 1>>(b);
 #elif TK == 1
   run_shape<rsort::SweepShape<384, 24, 2, 2>>(b);
   run_shape<rsort::SweepShape<256, 30, 3, 3, false, 300>>(b);
