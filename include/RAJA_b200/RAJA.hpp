@@ -9,6 +9,7 @@
 //     RAJA::b200_atomic                     (atomicAdd & friends)
 //     RAJA::b200_synchronize
 //     RAJA::b200_launch_t<Async>            (RAJA::launch, with or without expt::Reduce params)
+//     RAJA::b200_work<BLOCK, Async>, RAJA::unordered_b200_fused   (WorkPool / WorkGroup / WorkSite)
 //     RAJA::b200::{device,device_zeroed,pinned}_mempool_type
 //
 // usable with RAJA::forall (with or without RAJA::expt::Reduce / ReduceLoc / Name params),
@@ -78,5 +79,6 @@
 #include "RAJA_b200/reduce.hpp"
 #include "RAJA_b200/multi_reduce.hpp"
 #include "RAJA_b200/launch.hpp"
+#include "RAJA_b200/workgroup.hpp"
 
 #endif  // RAJA_B200_RAJA_HPP
