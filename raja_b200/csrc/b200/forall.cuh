@@ -51,8 +51,13 @@ forall_kernel(const __grid_constant__ Body body_in, const Index len, const __gri
   Body body = body_in;
   constexpr Index TILE = Index(BLOCK) * UNROLL;
   if constexpr (detail::has_tile<Body, Index, UNROLL>::value) {
-    // hand-written tile bodies (the streaming kernels of the C ABI): the compiler may software-pipeline across tiles
+    // hand-written tile bodies (the streaming kernels of the C ABI): the compiler may software-pipeline across tiles;
+    // the ragged last tile stays on one block (spreading it, as below, makes ptxas 12.9 settle on 32 registers and
+    // split the tile's eight loads into two groups: -2 % on triad / daxpy at 2^28)
     for (Index t = blockIdx.x; t < full_tiles; t += gridDim.x) body.template tile<UNROLL>(t * TILE + threadIdx.x, Index(BLOCK));
+    if (blockIdx.x == tail_owner) {
+      for (Index i = full_tiles * TILE + threadIdx.x; i < len; i += BLOCK) body(i);
+    }
   } else {
     // opaque bodies (user lambdas): the tile is already UNROLL-wide; unrolling this loop again costs a trip-count
     // division and 4x the code, which a forall of a few thousand indices pays for in instruction fetches
@@ -62,10 +67,8 @@ forall_kernel(const __grid_constant__ Body body_in, const Index len, const __gri
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) body(base + Index(u) * BLOCK);
     }
-  }
-  // ragged last tile (< TILE indices): its UNROLL chunks of BLOCK indices go to UNROLL different blocks, starting with
-  // the block that would own the next tile, so that a short loop costs ONE memory round trip, not UNROLL in sequence
-  {
+    // ragged last tile (< TILE indices): its UNROLL chunks of BLOCK indices go to UNROLL different blocks, starting with
+    // the block that would own the next tile, so that a short loop costs ONE memory round trip, not UNROLL in sequence
     const Index rem_base = full_tiles * TILE;
     const unsigned first = blockIdx.x >= tail_owner ? blockIdx.x - tail_owner : blockIdx.x + gridDim.x - tail_owner;
 #pragma unroll 1
