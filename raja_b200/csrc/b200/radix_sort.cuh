@@ -564,6 +564,7 @@ onesweep_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 // ---------------------------------------------------------------------------
 template <class U, bool FLOAT> struct RadixDigit {
   static constexpr bool PEER_OUT = false;
+  static constexpr int BUCKETS = RADIX;
   int shift;
   unsigned dxor;
   B200_D unsigned operator()(U k) const { return sweep_digit<FLOAT>(k, shift, dxor); }
@@ -571,6 +572,7 @@ template <class U, bool FLOAT> struct RadixDigit {
 constexpr int MAX_SPLITTERS = 7;
 template <class U> struct SplitDigit {
   static constexpr bool PEER_OUT = false;
+  static constexpr int BUCKETS = 8;  // MAX_SPLITTERS + 1: few, long runs per tile -> line-aligned write-out
   U s[MAX_SPLITTERS];  // already mapped with to_ordered(), non-decreasing
   int nsplit;
   KeyOrder order;
@@ -981,6 +983,40 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 #endif
 
   // ---- phase D: run-coalesced write-out ------------------------------------------------------------
+  if constexpr (DigitFn::BUCKETS <= 16 && !PACK) {
+    // Few buckets (splitter sweeps): a tile holds a handful of LONG runs.  Walk them one by one with the threads
+    // mapped onto the DESTINATION's 128-byte lines (thread t writes line offset t mod 32), so every warp store is one
+    // whole, aligned line except at the two ends of a run.  The rank-indexed loop below starts every run at an
+    // arbitrary element, i.e. every warp store straddles two lines and ends in partial sectors -- which is what
+    // costs over NVLink when the destination is a peer (the fused partition + all-to-all of the multi-GPU sort).
+    if (compute) {
+#pragma unroll 1
+      for (int d = 0; d < DigitFn::BUCKETS; ++d) {
+        const uint32_t cnt = s.count[d];
+        if (cnt == 0) continue;
+        const uint32_t r0 = s.texcl[d];
+        const G g0 = s.gbase[d] + (G)r0;  // position of the run's first element inside bucket d's destination
+        U* kd;
+        VT* vd = nullptr;
+        if constexpr (DigitFn::PEER_OUT) {
+          kd = digit.kdst[d] + g0;
+          if constexpr (HAS_VALUES) vd = digit.vdst[d] + g0;
+        } else {
+          kd = keys_out + g0;
+          if constexpr (HAS_VALUES) vd = vals_out + g0;
+        }
+        const uint32_t lead = (uint32_t)(((uintptr_t)kd / sizeof(U)) & 31u);
+        for (uint32_t i = (uint32_t)tid; i < lead + cnt; i += BLOCK) {
+          if (i >= lead) {
+            const uint32_t off = i - lead;
+            kd[off] = s.keys[r0 + off];
+            if constexpr (HAS_VALUES) vd[off] = s.vals[r0 + off];
+          }
+        }
+      }
+    }
+    return;
+  }
   if (compute) {
     const uint2* const pairs = reinterpret_cast<const uint2*>(s.keys);
     (void)pairs;
@@ -1153,12 +1189,40 @@ inline cudaError_t sort(cudaStream_t stream, U* keys, U* keys_alt, VT* vals, VT*
 template <class U, class DigitFn, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) bucket_count_kernel(const U* __restrict__ keys, const long long n, unsigned long long* __restrict__ ghist, const DigitFn digit)
 {
-  // per-thread counters for the 8 possible buckets, folded by warp shuffles, one global atomic per warp and bucket
+  // per-thread counters for the 8 possible buckets, folded by warp shuffles, one global atomic per warp and bucket.
+  // 128-bit loads, four per thread in flight (one scalar load per thread and iteration ran at a third of the HBM rate)
   unsigned c[MAX_SPLITTERS + 1] = {};
-  for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * BLOCK) {
-    const unsigned d = digit(ld_stream(keys + i));
+  auto count = [&](U k) {
+    const unsigned d = digit(k);
 #pragma unroll
     for (int b = 0; b <= MAX_SPLITTERS; ++b) c[b] += (d == (unsigned)b) ? 1u : 0u;
+  };
+  constexpr int VEC = 16 / sizeof(U), UNROLL = 4;
+  using V = Vec<U, VEC>;
+  long long head = (long long)(((16 - ((uintptr_t)keys & 15)) & 15) / sizeof(U));
+  if (head > n) head = n;
+  const long long nvec = (n - head) / VEC;
+  const V* const body = reinterpret_cast<const V*>(keys + head);
+  long long v = (long long)blockIdx.x * BLOCK * UNROLL + threadIdx.x;
+  const long long stride = (long long)gridDim.x * BLOCK * UNROLL;
+  for (; v + (UNROLL - 1) * BLOCK < nvec; v += stride) {
+    V x[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) x[u] = ld_stream(body + v + u * BLOCK);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) count(x[u].e[e]);
+  }
+  for (int u = 0; u < UNROLL; ++u)
+    if (v + u * BLOCK < nvec) {
+      const V x = ld_stream(body + v + u * BLOCK);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) count(x.e[e]);
+    }
+  if (blockIdx.x == 0) {  // unaligned head and the tail shorter than one vector
+    for (long long i = threadIdx.x; i < head; i += BLOCK) count(keys[i]);
+    for (long long i = head + nvec * VEC + threadIdx.x; i < n; i += BLOCK) count(keys[i]);
   }
 #pragma unroll
   for (int b = 0; b <= MAX_SPLITTERS; ++b) {
@@ -1197,7 +1261,7 @@ inline cudaError_t bucket_counts(cudaStream_t stream, const U* keys_in, long lon
   if (e != cudaSuccess) return e;
   if (n > 0) {
     constexpr int CB = 512;
-    long long grid = (n + CB * 8 - 1) / (CB * 8);
+    long long grid = (n + CB * 16 - 1) / (CB * 16);
     const long long cap = (long long)device_info().sm_count * 4;
     if (grid > cap) grid = cap;
     LaunchScope scope("bucket_count_kernel", stream);

@@ -103,7 +103,7 @@ class PeerComm:
 
     def capacity(self, key_bytes, val_bytes):
         """elements the receive buffers of one exchange can take"""
-        return max((self.nbytes - self.header - 64) // (key_bytes + val_bytes), 0)
+        return max((self.nbytes - self.header - 128) // (key_bytes + val_bytes), 0)
 
     def exchange_pairs(self, keys, vals, splitters, descending, res):
         """fused partition + all-to-all -> (keys_recv, vals_recv): views of this rank's receive buffers,
@@ -115,7 +115,7 @@ class PeerComm:
         ks, vb = keys.element_size(), (vals.element_size() if vals is not None else 0)
         cap = self.capacity(ks, vb)
         koff = self.header
-        voff = koff + ((cap * ks + 63) // 64) * 64
+        voff = koff + ((cap * ks + 127) // 128) * 128  # 128-byte aligned: the split sweep writes whole lines
         dt = api._dt(keys)
         sp = np.ascontiguousarray(np.asarray(splitters, dtype=api._NP[dt]))
         got = ctypes.c_int64(0)
