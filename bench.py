@@ -36,7 +36,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "hot-path throughput: forall+ReduceSum(dot f64) + inclusive_scan(i32) + sort_pairs(u32,u32) @2^28 per GPU"
 BYTES_DOT, BYTES_SCAN, BYTES_SORT_MODEL, BYTES_SORT_LOWER = 16, 8, 68, 16
 BYTES_ONESWEEP_PASS = 16  # one onesweep launch: read K+V, write K+V
-NCU_ONESWEEP_TRAFFIC = 4.289e9  # bytes per launch measured by ncu at N=2^28 (2.166 GB read + 2.123 GB written, profiles/r01_onesweep_v3_ncu.txt)
+NCU_ONESWEEP_TRAFFIC = 4.289e9  # bytes per launch measured by ncu at N=2^28 (2.169 GB read + 2.120 GB written, profiles/r01_onesweep_v4_ncu.txt)
 
 
 def peaks():
@@ -324,7 +324,7 @@ def run_b200(args):
         "paths": paths,
         "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (one radix pass, u32 keys + u32 values)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N=2^28 (ncu --set full, profiles/r01_onesweep_v3_ncu.txt)
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N=2^28 (ncu --set full, profiles/r01_onesweep_v4_ncu.txt)
                      "traffic": NCU_ONESWEEP_TRAFFIC if args.log2n == 28 else None, "peak_source": peak_src,
                      "bytes_per_launch": n * BYTES_ONESWEEP_PASS, "avg_launch_ms": pass_ms},
         "kernels": kern,

@@ -59,5 +59,18 @@ for it in range(4):
 if rank == 0:
     for k, v in acc.items():
         print(f"{k:60s} {v / 2:8.3f} ms")
+# per-kernel times of one more whole sort (event-bracketed launches: rb200_profile_*)
+import ctypes
+from raja_b200._lib import lib
+keys2 = keys.clone(); vals2 = vals.clone(); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+lib.rb200_profile_reset(); lib.rb200_profile_enable(1)
+multi.sort_pairs(rng, keys2, vals2, ops=ops, keys_alt=ka, vals_alt=va)
+torch.cuda.synchronize()
+lib.rb200_profile_enable(0)
+if rank == 0:
+    tot, cnt = ctypes.c_double(), ctypes.c_longlong()
+    for name in (b"bucket_count_kernel", b"peer_allgather_kernel", b"scan_bins_kernel", b"histogram_kernel", b"onesweep_kernel"):
+        lib.rb200_profile_query(name, ctypes.byref(tot), ctypes.byref(cnt))
+        print(f"kernel {name.decode():28s} launches {cnt.value:3d} total {tot.value:8.3f} ms")
 comm.close()
 dist.destroy_process_group()
