@@ -354,6 +354,29 @@ def test_partition_pairs_is_the_stable_split(rb, dtype, desc):
             assert np.array_equal(host(vo), ev), (n, nsplit)
 
 
+@pytest.mark.parametrize("dtype", [np.uint32, np.float64])
+@pytest.mark.parametrize("shift", [1, 3, 17])
+def test_partition_pairs_unaligned_pointers(rb, dtype, shift):
+    """input and output pointers that are not 16-byte / 128-byte aligned: the line-aligned write-out of the splitter sweep
+    (threads mapped onto the destination's 128-byte lines) and the 128-bit loads of the bucket count must handle the heads"""
+    n, nsplit = 300_007, 5
+    k = data(dtype, n, 4242 + shift, -1000, 1000)
+    sp = np.sort(np.random.default_rng(shift).choice(k, size=nsplit, replace=False))
+    v = np.arange(n).astype(np.uint32)
+    kin = torch.empty(n + 64, dtype=dev(k).dtype, device="cuda")[shift:shift + n]
+    kin.copy_(dev(k))
+    vin = torch.empty(n + 64, dtype=torch.uint32, device="cuda")[shift + 1:shift + 1 + n]
+    vin.copy_(dev(v))
+    ko = torch.empty(n + 64, dtype=kin.dtype, device="cuda")[shift + 2:shift + 2 + n]
+    vo = torch.empty(n + 64, dtype=torch.uint32, device="cuda")[shift:shift + n]
+    counts = torch.zeros(8, dtype=torch.int64, device="cuda")
+    rb.partition_pairs(kin, ko, vin, vo, sp, counts, 0)
+    ek, ev, ec = _np_partition(k, v, sp, False)
+    assert np.array_equal(host(counts), ec)
+    assert np.array_equal(host(ko).view(np.uint8), ek.view(np.uint8))
+    assert np.array_equal(host(vo), ev)
+
+
 def test_partition_pairs_rejects_bad_arguments(rb):
     k = dev(np.arange(10, dtype=np.uint32))
     counts = torch.zeros(8, dtype=torch.int64, device="cuda")
