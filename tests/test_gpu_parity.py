@@ -480,3 +480,14 @@ def test_full_size_sort_pairs_properties(rb):
     assert bool((v[1:][same] > v[:-1][same]).all())                       # stable: ties keep input order
     assert bool((orig.view(torch.int32)[v.long()] == k).all())            # every pair still matches its key
     assert int(v.sum(dtype=torch.int64)) == N_FULL * (N_FULL - 1) // 2    # values are a permutation (checksum)
+
+
+def test_sort_beyond_2_30_elements_uses_64_bit_lookback():
+    """n >= 2^30 switches the look-back words to 64 bits (radix_sort.cuh: C = unsigned long long); size-independent properties at
+    2^30 + 12345 keys: sortedness, checksum, values = the matching permutation, stability (tools/micro/big_sort_check.py)"""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if torch.cuda.get_device_properties(0).total_memory < 60 * 2**30:
+        pytest.skip("needs ~40 GB of device memory")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "micro", "big_sort_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "BIG SORT OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
