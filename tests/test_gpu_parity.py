@@ -491,3 +491,14 @@ def test_sort_beyond_2_30_elements_uses_64_bit_lookback():
         pytest.skip("needs ~40 GB of device memory")
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "micro", "big_sort_check.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "BIG SORT OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_scan_beyond_2_31_elements():
+    """64-bit lengths (the reference's CUDA scans take int): inclusive / exclusive scan of 2^31 + 7 int32 elements, checked element by
+    element through out[i] - out[i-1] == in[i] and an independent 64-bit total (tools/micro/big_scan_check.py)"""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if torch.cuda.get_device_properties(0).total_memory < 60 * 2**30:
+        pytest.skip("needs ~30 GB of device memory")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "micro", "big_scan_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "BIG SCAN OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
