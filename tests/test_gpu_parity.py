@@ -502,3 +502,14 @@ def test_scan_beyond_2_31_elements():
         pytest.skip("needs ~30 GB of device memory")
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "micro", "big_scan_check.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "BIG SCAN OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_forall_and_reducers_beyond_2_31_elements():
+    """64-bit index spaces: ReduceSum / MinLoc / MaxLoc with the extrema (and their duplicates) planted past index 2^31, triad over
+    2^31 + 5 floats (tools/micro/big_reduce_check.py)"""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if torch.cuda.get_device_properties(0).total_memory < 60 * 2**30:
+        pytest.skip("needs ~40 GB of device memory")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "micro", "big_reduce_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "BIG REDUCE OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
