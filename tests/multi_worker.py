@@ -167,7 +167,9 @@ def main():
         # ---- sample sort: the concatenation over ranks must equal the oracle's stable sort
         for keys in (rng_np.integers(0, 2**32, n_global, dtype=np.uint64).astype(np.uint32),
                      (rng_np.integers(0, 2**32, n_global, dtype=np.uint64) & 0x7).astype(np.uint32),   # heavy duplicates
-                     rng_np.integers(-50, 50, n_global).astype(np.int32)):
+                     rng_np.integers(-50, 50, n_global).astype(np.int32),
+                     (rng_np.integers(-2000, 2000, n_global) / 8.0).astype(np.float64),                 # floating keys, duplicates, both signs
+                     rng_np.standard_normal(n_global).astype(np.float32)):
             vals = np.arange(n_global, dtype=np.uint32)
             for desc in (False, True):
                 ko, vo = multi.sort_pairs(sr, T(keys[lo:hi].copy()), T(vals[lo:hi].copy()), descending=desc, ops=ops)
