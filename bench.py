@@ -39,6 +39,12 @@ BYTES_ONESWEEP_PASS = 16  # one onesweep launch: read K+V, write K+V
 NCU_ONESWEEP_TRAFFIC = 4.289e9  # bytes per launch measured by ncu at N=2^28 (2.169 GB read + 2.120 GB written, profiles/r01_onesweep_v4_ncu.txt)
 
 
+def workload_config(log2n):
+    """the same dict on both arms (b200 and --impl reference), so the two lines describe one configuration"""
+    return {"workload": f"dot(f64)+inclusive_scan(i32)+sort_pairs(u32,u32), N=2^{log2n} elements per path per GPU (rank)",
+            "l2": "inputs (1-2 GiB each) larger than the 126 MB L2; every step sorts fresh unsorted buffers"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -149,10 +155,18 @@ def cpu_step(ref, data):
     return {"dot": t_dot, "scan": t2 - t1, "sort": t4 - t3}
 
 
+def host_threads():
+    """cores this process may run on (torchrun exports OMP_NUM_THREADS=1, so the OpenMP default is not it)"""
+    try:
+        return max(len(os.sched_getaffinity(0)), 1)
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference(log2n, steps, warmup):
     from oracle_lib import Oracle, Reference
     if Reference.available():
-        ref = Reference(1)  # omp_parallel_for_exec with every host thread
+        ref = Reference(1, threads=host_threads())  # omp_parallel_for_exec with every host thread, set explicitly
         what = "RAJA omp_parallel_for_exec/omp_reduce from oracle/_ref (reference headers, g++ -O2 -fopenmp)"
     else:
         ref = Oracle()
@@ -176,6 +190,95 @@ def cpu_reference(log2n, steps, warmup):
             "sample": f"same 3-path step at N=2^{log2n} per path ({what}); GB/s uses the same algorithmic bytes/element",
             "paths": paths}
 
+
+
+# --------------------------------------------------------------------------------------- verification (outside the timed region)
+def verify_step(rb, rbm, sharded, n, dev, res, world, rank, seed=987):
+    """One more step on fresh inputs whose results are CHECKED on the device (torch ops here are the checker, not
+    the product): every rank's piece of the sort is sorted and stable, pieces are ordered across ranks, nothing
+    was lost or duplicated (count, pair checksum), the scan equals an int64 cumsum seeded with the lower ranks'
+    totals, the dot agrees with an fp64 all-reduce.  Returns a dict of booleans; bench.py exits non-zero on any False."""
+    import torch
+    import torch.distributed as dist
+    from raja_b200._lib import lib
+    g = torch.Generator(device=dev).manual_seed(seed + rank)
+    apol = rb.b200_exec(async_=True)
+    out = {}
+
+    def allsum(t):
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+
+    # ---- dot
+    x = torch.rand(n, dtype=torch.float64, device=dev, generator=g) + 0.5
+    y = torch.rand(n, dtype=torch.float64, device=dev, generator=g) + 0.5
+    if sharded:
+        got = rbm.reduce_dot(sharded, x, y, res=res, as_tensor=True).reshape(1).clone()
+    else:
+        pin = rb.PinnedBuffer(16)
+        rb._lib.check(lib.rb200_reduce_dot(rb._lib.F64, x.data_ptr(), y.data_ptr(), n, pin.ptr, res.handle), "dot")
+        torch.cuda.synchronize()
+        got = torch.tensor([float(pin.view("float64")[0])], dtype=torch.float64, device=dev)
+    want = allsum(torch.dot(x, y).reshape(1))  # all positive: sum |x y| == the dot itself
+    tol = world * n * torch.finfo(torch.float64).eps * want
+    out["dot"] = bool((got - want).abs() <= tol)
+    del x, y
+
+    # ---- scan: int64 cumsum of the shard + the lower ranks' totals, wrapped to int32 like the device arithmetic
+    s_in = torch.randint(0, 8, (n,), dtype=torch.int32, device=dev, generator=g)
+    s_out = torch.empty_like(s_in)
+    if sharded:
+        rbm.inclusive_scan(sharded, s_in, s_out, res=res)
+    else:
+        rb.inclusive_scan(s_in, s_out, pol=apol, res=res)
+    tot = s_in.sum(dtype=torch.int64).reshape(1)
+    totals = torch.zeros(world, dtype=torch.int64, device=dev)
+    totals[rank] = tot[0]
+    allsum(totals)
+    carry = totals[:rank].sum()
+    want = (torch.cumsum(s_in, 0, dtype=torch.int64) + carry).to(torch.int32)
+    out["scan"] = bool(torch.equal(want, s_out))
+    del s_in, s_out, want
+
+    # ---- sort_pairs: values carry the GLOBAL original index, so stability is checkable across ranks
+    k = torch.randint(-2**31, 2**31, (n,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+    k[::5] &= 0xFFFF  # duplicates, so that stability is exercised
+    v = (torch.arange(n, dtype=torch.int64, device=dev) + rank * n).to(torch.int32)
+    k64 = k.to(torch.int64) & 0xFFFFFFFF
+    v64 = v.to(torch.int64) & 0xFFFFFFFF
+    chk_in = allsum(torch.stack([(k64 * (v64 + 1)).sum(), k64.sum(), v64.sum()]))  # int64 arithmetic wraps: a checksum
+    del k64, v64
+    ka, va = torch.empty_like(k), torch.empty_like(v)
+    ku, vu = k.view(torch.uint32), v.view(torch.uint32)
+    if sharded:
+        ko, vo = rbm.sort_pairs(sharded, ku, vu, res=res, keys_alt=ka.view(torch.uint32), vals_alt=va.view(torch.uint32))
+    else:
+        rb.sort_pairs(ku, vu, pol=apol, res=res, keys_alt=ka.view(torch.uint32), vals_alt=va.view(torch.uint32))
+        ko, vo = ku, vu
+    torch.cuda.synchronize()
+    m = ko.numel()
+    ko64 = ko.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    vo64 = vo.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    chk_out = allsum(torch.stack([(ko64 * (vo64 + 1)).sum(), ko64.sum(), vo64.sum()]))
+    count = allsum(torch.tensor([m], dtype=torch.int64, device=dev))
+    ok_sorted = bool((ko64[1:] >= ko64[:-1]).all()) if m > 1 else True
+    ok_stable = bool(((ko64[1:] != ko64[:-1]) | (vo64[1:] > vo64[:-1])).all()) if m > 1 else True
+    # piece boundaries: (last key, last value) of rank r sorts before (first key, first value) of the next non-empty rank
+    edge = torch.zeros(world, 5, dtype=torch.int64, device=dev)
+    if m > 0:
+        edge[rank] = torch.stack([ko64[0], vo64[0], ko64[-1], vo64[-1], torch.tensor(m, device=dev)])
+    allsum(edge)
+    e = [r for r in edge.tolist() if r[4] > 0]
+    ok_edges = all((a[2], a[3]) < (b[0], b[1]) for a, b in zip(e, e[1:]))
+    flags = allsum(torch.tensor([int(not ok_sorted), int(not ok_stable)], dtype=torch.int64, device=dev))
+    out["sort_sorted"] = int(flags[0]) == 0
+    out["sort_stable"] = int(flags[1]) == 0
+    out["sort_boundaries"] = bool(ok_edges)
+    out["sort_count"] = int(count[0]) == world * n
+    out["sort_checksum"] = bool(torch.equal(chk_in, chk_out))
+    out["sort_piece_sizes"] = [int(r[4]) for r in edge.tolist()]
+    return out
 
 # --------------------------------------------------------------------------------------- b200 arm
 def run_b200(args):
@@ -302,9 +405,21 @@ def run_b200(args):
     if not args.no_e2e:
         e2e = run_e2e(rb, rbm, sharded, n, dev, stream, res, world, barrier, min(K, args.e2e_steps))
 
+    # ---- results checked on the device, every rank (outside the timed region)
+    verified = None
+    if not args.no_verify:
+        del sort_sets[:]
+        torch.cuda.empty_cache()
+        verified = verify_step(rb, rbm, sharded, n, dev, res, world, rank)
+        verified["all"] = all(v for k, v in verified.items() if isinstance(v, bool))
+
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if verified is not None and not verified["all"]:
+        print(f"bench.py: rank {rank}: VERIFICATION FAILED: {verified}", file=sys.stderr, flush=True)
+        if rank != 0:
+            raise SystemExit(3)
     if rank != 0:
         return
     peak, peak_src = peaks()
@@ -319,21 +434,22 @@ def run_b200(args):
     achieved = n * BYTES_ONESWEEP_PASS / pass_ms / 1e6 if pass_ms else None
     cpu = None
     if world == 1 and not args.no_cpu:
-        c = cpu_reference(args.cpu_log2n, 2, 1)
+        c = cpu_reference(args.cpu_log2n, 1, 1)
         cpu = {"value": c["value"], "unit": "GB/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"], "paths": c["paths"]}
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32+u32", "data": "synthetic",
-        "config": {"workload": f"dot(f64)+inclusive_scan(i32)+sort_pairs(u32,u32), N=2^{args.log2n} elements per path per GPU",
-                   "l2": "inputs (1-2 GiB each) larger than the 126 MB L2; every step sorts fresh unsorted buffers",
-                   "prewarm": "0.3 s of untimed dot+scan in front of the W warm-up steps",
-                   "sharding": "none" if world == 1 else ("contiguous shards; allreduce(dot), carry allgather(scan), sample-sort all-to-all(sort); exchanges by " +
-                                                           ("NCCL collectives" if args.nccl_exchange else "the NVLink peer-memory communicator (sort: fused partition + all-to-all sweep)"))},
+        "config": workload_config(args.log2n),
+        "run": {"prewarm": "0.3 s of untimed dot+scan in front of the W warm-up steps",
+                "sharding": "none" if world == 1 else ("contiguous shards; allreduce(dot), carry allgather(scan), sample-sort all-to-all(sort); exchanges by " +
+                                                        ("NCCL collectives" if args.nccl_exchange else "the NVLink peer-memory communicator (sort: fused partition + all-to-all sweep)"))},
+        "verified": verified["all"] if verified is not None else None, "verification": verified,
         "paths": paths,
         "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (one radix pass, u32 keys + u32 values)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak if achieved else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N=2^28 (ncu --set full, profiles/r01_onesweep_v4_ncu.txt)
-                     "traffic": NCU_ONESWEEP_TRAFFIC if args.log2n == 28 else None, "peak_source": peak_src,
+                     "traffic": NCU_ONESWEEP_TRAFFIC if args.log2n == 28 else None, "traffic_source": "from_profile (ncu --set full of this kernel at this N, not re-measured in this run)",
+                     "peak_source": peak_src,
                      "bytes_per_launch": n * BYTES_ONESWEEP_PASS, "avg_launch_ms": pass_ms},
         "kernels": kern,
         "cpu_baseline": cpu,
@@ -342,7 +458,9 @@ def run_b200(args):
         "wall_ms_per_step": t_wall * 1e3 / K,
         "clocks": clocks,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    if verified is not None and not verified["all"]:
+        raise SystemExit(3)
 
 
 def run_e2e(rb, rbm, sharded, n, dev, stream, res, world, barrier, steps):
@@ -459,7 +577,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": c["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": c["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32+u32",
             "data": "synthetic",
-            "config": {"workload": f"dot(f64)+inclusive_scan(i32)+sort_pairs(u32,u32), bounded sample N=2^{args.cpu_log2n} per path on the host cores"},
+            "config": workload_config(args.cpu_log2n),
+            "run": {"sample": f"each step = one pass over N=2^{args.cpu_log2n} per path on the host cores ({c['cores']} OpenMP threads, set explicitly); rank 0 only"},
             "paths": c["paths"],
             "cpu_baseline": {"value": c["value"], "unit": "GB/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"]},
             "e2e": {"value": c["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -473,13 +592,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log2n", type=int, default=28)
-    ap.add_argument("--cpu-log2n", type=int, default=24)
+    ap.add_argument("--cpu-log2n", type=int, default=None, help="N of the CPU arm (default: --log2n, the GPU arm's N)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the checked step after the timed region")
     ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: exchange with NCCL collectives instead of the peer-memory communicator")
     args = ap.parse_args()
+    if args.cpu_log2n is None:
+        args.cpu_log2n = args.log2n
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -144,6 +144,8 @@ template <class T> using Omp = Ops<RAJA::omp_parallel_for_exec, RAJA::omp_reduce
 extern "C" {
 
 int ref_omp_max_threads(void) { return omp_get_max_threads(); }
+// launchers such as torchrun export OMP_NUM_THREADS=1: the timed baseline sets its thread count explicitly
+void ref_omp_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 const char* ref_version(void) { return "RAJA " RAJA_STRINGIFY(RAJA_VERSION_MAJOR) "." RAJA_STRINGIFY(RAJA_VERSION_MINOR) "." RAJA_STRINGIFY(RAJA_VERSION_PATCHLEVEL); }
 
 #define DEF(S, T)                                                                                                        \

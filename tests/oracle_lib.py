@@ -145,12 +145,16 @@ class Reference(_Base):
     prefix = "ref"
     kind = "reference"
 
-    def __init__(self, pol=0):
+    def __init__(self, pol=0, threads=None):
         if not os.path.exists(REF_SO):
             raise FileNotFoundError(REF_SO)
         self.lib = ctypes.CDLL(REF_SO)
         self.pol_args = (pol,)
         self.lib.ref_omp_max_threads.restype = ctypes.c_int
+        if threads and pol != 0:
+            # explicit: launchers (torchrun) export OMP_NUM_THREADS=1 to their children
+            self.lib.ref_omp_set_num_threads.argtypes = [ctypes.c_int]
+            self.lib.ref_omp_set_num_threads(int(threads))
         self.cores = 1 if pol == 0 else self.lib.ref_omp_max_threads()
 
     @staticmethod
