@@ -192,8 +192,84 @@ def cpu_reference(log2n, steps, warmup):
 
 
 
+
+# --------------------------------------------------------------------------------------- how one rank runs the three paths
+POLICY_SO = os.path.join(ROOT, "bench", "_build", "libpolicy_bench.so")
+
+
+class PolicyLib:
+    """bench/_build/libpolicy_bench.so: RAJA::forall / inclusive_scan / sort_pairs instantiated with user-style lambdas for
+    the b200 policies (the public API a RAJA user calls) and for the reference's own CUDA back-end (cuda_exec + CUB)."""
+
+    def __init__(self):
+        self.lib = ctypes.CDLL(POLICY_SO)
+        self.lib.pb_last_error.restype = ctypes.c_char_p
+        P, L, D = ctypes.c_void_p, ctypes.c_long, ctypes.c_double
+        for name in ("pb_dot_expt", "pb_dot_classic"):
+            for arm in ("b200", "cuda"):
+                getattr(self.lib, f"{name}_{arm}").argtypes = [P, P, L, ctypes.POINTER(D), P]
+        for arm in ("b200", "cuda"):
+            getattr(self.lib, f"pb_inclusive_scan_{arm}").argtypes = [P, P, L, P]
+            getattr(self.lib, f"pb_sort_pairs_{arm}").argtypes = [P, P, L, P]
+            getattr(self.lib, f"pb_triad_{arm}").argtypes = [P, P, P, D, L, P]
+            getattr(self.lib, f"pb_stable_sort_f64_{arm}").argtypes = [P, L, P]
+        for name in ("pb_histogram_b200", "pb_histogram_aggregated_b200", "pb_histogram_cuda"):
+            getattr(self.lib, name).argtypes = [P, P, L, P]
+
+    @staticmethod
+    def available():
+        return os.path.exists(POLICY_SO)
+
+    def call(self, name, *args):
+        if getattr(self.lib, name)(*args) != 0:
+            raise RuntimeError(f"{name}: {self.lib.pb_last_error().decode()}")
+
+
+class Paths:
+    """dot / scan / sort_pairs of one rank, by one of three routes:
+       policy   RAJA front-ends + b200 policies (user lambdas, pools, resource: the public C++ API)
+       cabi     the C ABI of libraja_b200.so (named loop bodies of the same engine)
+       cuda     RAJA front-ends + the reference's cuda_exec / cuda_reduce / CUB ("the kernels to beat")"""
+
+    def __init__(self, kind, rb, res, pb=None):
+        self.kind, self.rb, self.res, self.pb = kind, rb, res, pb
+        self.out = ctypes.c_double(0.0)
+        self.pin = rb.PinnedBuffer(16) if kind == "cabi" else None
+        self.apol = rb.b200_exec(async_=True)
+
+    def dot(self, x, y):
+        n = x.numel()
+        if self.kind == "cabi":
+            from raja_b200._lib import lib
+            self.rb._lib.check(lib.rb200_reduce_dot(self.rb._lib.F64, x.data_ptr(), y.data_ptr(), n, self.pin.ptr, self.res.handle), "dot")
+        else:
+            arm = "b200" if self.kind == "policy" else "cuda"
+            self.pb.call(f"pb_dot_expt_{arm}", x.data_ptr(), y.data_ptr(), n, ctypes.byref(self.out), self.res.handle)
+
+    def dot_value(self):
+        """host value of the last dot (cabi: after a stream sync)"""
+        if self.kind == "cabi":
+            self.res.wait()
+            return float(self.pin.view("float64")[0])
+        return float(self.out.value)
+
+    def scan(self, src, dst):
+        if self.kind == "cabi":
+            self.rb.inclusive_scan(src, dst, pol=self.apol, res=self.res)
+        else:
+            arm = "b200" if self.kind == "policy" else "cuda"
+            self.pb.call(f"pb_inclusive_scan_{arm}", src.data_ptr(), dst.data_ptr(), src.numel(), self.res.handle)
+
+    def sort_pairs(self, k, v, k_alt=None, v_alt=None):
+        if self.kind == "cabi":
+            self.rb.sort_pairs(k, v, pol=self.apol, res=self.res, keys_alt=k_alt, vals_alt=v_alt)
+        else:
+            arm = "b200" if self.kind == "policy" else "cuda"
+            self.pb.call(f"pb_sort_pairs_{arm}", k.data_ptr(), v.data_ptr(), k.numel(), self.res.handle)
+
+
 # --------------------------------------------------------------------------------------- verification (outside the timed region)
-def verify_step(rb, rbm, sharded, n, dev, res, world, rank, seed=987):
+def verify_step(rb, rbm, sharded, paths, n, dev, res, world, rank, seed=987):
     """One more step on fresh inputs whose results are CHECKED on the device (torch ops here are the checker, not
     the product): every rank's piece of the sort is sorted and stable, pieces are ordered across ranks, nothing
     was lost or duplicated (count, pair checksum), the scan equals an int64 cumsum seeded with the lower ranks'
@@ -216,10 +292,8 @@ def verify_step(rb, rbm, sharded, n, dev, res, world, rank, seed=987):
     if sharded:
         got = rbm.reduce_dot(sharded, x, y, res=res, as_tensor=True).reshape(1).clone()
     else:
-        pin = rb.PinnedBuffer(16)
-        rb._lib.check(lib.rb200_reduce_dot(rb._lib.F64, x.data_ptr(), y.data_ptr(), n, pin.ptr, res.handle), "dot")
-        torch.cuda.synchronize()
-        got = torch.tensor([float(pin.view("float64")[0])], dtype=torch.float64, device=dev)
+        paths.dot(x, y)
+        got = torch.tensor([paths.dot_value()], dtype=torch.float64, device=dev)
     want = allsum(torch.dot(x, y).reshape(1))  # all positive: sum |x y| == the dot itself
     tol = world * n * torch.finfo(torch.float64).eps * want
     out["dot"] = bool((got - want).abs() <= tol)
@@ -231,7 +305,7 @@ def verify_step(rb, rbm, sharded, n, dev, res, world, rank, seed=987):
     if sharded:
         rbm.inclusive_scan(sharded, s_in, s_out, res=res)
     else:
-        rb.inclusive_scan(s_in, s_out, pol=apol, res=res)
+        paths.scan(s_in, s_out)
     tot = s_in.sum(dtype=torch.int64).reshape(1)
     totals = torch.zeros(world, dtype=torch.int64, device=dev)
     totals[rank] = tot[0]
@@ -254,7 +328,7 @@ def verify_step(rb, rbm, sharded, n, dev, res, world, rank, seed=987):
     if sharded:
         ko, vo = rbm.sort_pairs(sharded, ku, vu, res=res, keys_alt=ka.view(torch.uint32), vals_alt=va.view(torch.uint32))
     else:
-        rb.sort_pairs(ku, vu, pol=apol, res=res, keys_alt=ka.view(torch.uint32), vals_alt=va.view(torch.uint32))
+        paths.sort_pairs(ku, vu, ka.view(torch.uint32), va.view(torch.uint32))
         ko, vo = ku, vu
     torch.cuda.synchronize()
     m = ko.numel()
@@ -327,26 +401,51 @@ def run_b200(args):
     stream = torch.cuda.current_stream()
     res = rb.Resource(stream)
     apol = rb.b200_exec(async_=True)
-    dot_out = rb.PinnedBuffer(16)
+    # one GPU: the three paths go through the RAJA front-ends with the b200 policies (user lambdas in a C++ translation
+    # unit: bench/policy_bench.cu) -- the public API; --route cabi keeps the C-ABI bodies.  Several GPUs: the sharded layer.
+    pb = PolicyLib() if PolicyLib.available() else None
+    route = args.route or ("policy" if pb is not None else "cabi")
+    if route == "policy" and pb is None:
+        raise SystemExit("bench.py: --route policy needs bench/_build/libpolicy_bench.so (built by __graft_entry__.build())")
+    paths = Paths(route, rb, res, pb)
 
-    def step(i, ev=None):
-        k, v = sort_sets[i]
+    def run_step(pth, k, v, ev=None):
         if ev: ev[0].record(stream)
         if sharded:
             rbm.reduce_dot(sharded, x, y, res=res, as_tensor=True)
         else:
-            rb._lib.check(lib.rb200_reduce_dot(rb._lib.F64, x.data_ptr(), y.data_ptr(), n, dot_out.ptr, res.handle), "dot")
+            pth.dot(x, y)
         if ev: ev[1].record(stream)
         if sharded:
             rbm.inclusive_scan(sharded, s_in, s_out, res=res)
         else:
-            rb.inclusive_scan(s_in, s_out, pol=apol, res=res)
+            pth.scan(s_in, s_out)
         if ev: ev[2].record(stream)
         if sharded:
             rbm.sort_pairs(sharded, k, v, res=res, keys_alt=k_alt, vals_alt=v_alt)
         else:
-            rb.sort_pairs(k, v, pol=apol, res=res, keys_alt=k_alt, vals_alt=v_alt)
+            pth.sort_pairs(k, v, k_alt, v_alt)
         if ev: ev[3].record(stream)
+
+    def step(i, ev=None):
+        run_step(paths, *sort_sets[i], ev=ev)
+
+    def timed_arm(pth, steps, warm):
+        """a few steps of another route over re-randomised sort buffers (single GPU, after the headline region)"""
+        for i in range(steps + warm):
+            k, v = sort_sets[i]
+            k.view(torch.int32).copy_(torch.randint(-2**31, 2**31, (n,), dtype=torch.int64, device=dev, generator=g).to(torch.int32))
+            v.view(torch.int32).copy_(torch.arange(n, dtype=torch.int32, device=dev))
+        for i in range(warm):
+            run_step(pth, *sort_sets[i])
+        torch.cuda.synchronize()
+        es = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+        for i in range(steps):
+            run_step(pth, *sort_sets[warm + i], ev=es[i])
+        torch.cuda.synchronize()
+        t = [sum(e[j].elapsed_time(e[j + 1]) for e in es) / steps for j in range(3)]
+        return {"dot_ms": t[0], "scan_ms": t[1], "sort_pairs_ms": t[2], "step_ms": sum(t), "steps": steps,
+                "value_gbs": n * (BYTES_DOT + BYTES_SCAN + BYTES_SORT_MODEL) / sum(t) / 1e6}
 
     def barrier():
         if world > 1:
@@ -357,8 +456,8 @@ def run_b200(args):
     # which leave the per-step sort buffers untouched
     t_pre = time.perf_counter()
     while time.perf_counter() - t_pre < 0.3:
-        rb._lib.check(lib.rb200_reduce_dot(rb._lib.F64, x.data_ptr(), y.data_ptr(), n, dot_out.ptr, res.handle), "dot")
-        rb.inclusive_scan(s_in, s_out, pol=apol, res=res)
+        paths.dot(x, y)
+        paths.scan(s_in, s_out)
         torch.cuda.synchronize()
     for i in range(W):
         step(i)
@@ -396,21 +495,32 @@ def run_b200(args):
     lib.rb200_profile_query(b"onesweep_kernel", ctypes.byref(tot), ctypes.byref(cnt))
     pass_ms = tot.value / max(cnt.value, 1)
     kern = {}
-    for name in (b"forall_reduce_kernel", b"scan_kernel", b"histogram_kernel", b"onesweep_kernel"):
+    for name in (b"forall_reduce_kernel", b"forall_kernel", b"scan_kernel", b"histogram_kernel", b"onesweep_kernel"):
         lib.rb200_profile_query(name, ctypes.byref(tot), ctypes.byref(cnt))
         kern[name.decode()] = {"launches": cnt.value, "avg_ms": tot.value / max(cnt.value, 1), "share_of_step": tot.value / K / step_ms if step_ms else None}
+
+    # ---- one GPU: the same step by the other routes, same process, same buffers: the reference's own CUDA back-end
+    #      (cuda_exec + cuda_reduce + CUB: "the kernels to beat") and the C ABI
+    reference_gpu = cabi = None
+    if world == 1 and pb is not None and not args.no_reference_gpu:
+        reference_gpu = timed_arm(Paths("cuda", rb, res, pb), min(K, 5), 2)
+        reference_gpu["what"] = ("RAJA::forall<cuda_exec_async<256>> + expt::Reduce<plus>, RAJA::inclusive_scan<cuda_exec> (cub::DeviceScan), "
+                                 "RAJA::sort_pairs<cuda_exec> (cub::DeviceRadixSort), unmodified reference headers, same lambdas and buffers")
+        other = "cabi" if route == "policy" else "policy"
+        cabi = timed_arm(Paths(other, rb, res, pb), min(K, 5), 2)
+        cabi["route"] = other
 
     # ---- e2e: same step from pinned host buffers through the public API
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(rb, rbm, sharded, n, dev, stream, res, world, barrier, min(K, args.e2e_steps))
+        e2e = run_e2e(rb, rbm, sharded, paths, n, dev, stream, res, world, barrier, min(K, args.e2e_steps))
 
     # ---- results checked on the device, every rank (outside the timed region)
     verified = None
     if not args.no_verify:
         del sort_sets[:]
         torch.cuda.empty_cache()
-        verified = verify_step(rb, rbm, sharded, n, dev, res, world, rank)
+        verified = verify_step(rb, rbm, sharded, paths, n, dev, res, world, rank)
         verified["all"] = all(v for k, v in verified.items() if isinstance(v, bool))
 
     if world > 1:
@@ -440,7 +550,11 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32+u32", "data": "synthetic",
         "config": workload_config(args.log2n),
-        "run": {"prewarm": "0.3 s of untimed dot+scan in front of the W warm-up steps",
+        "run": {"route": ("sharded layer (raja_b200/multi.py over the C ABI)" if world > 1 else
+                          {"policy": "RAJA::forall<b200_exec_async<256>> + expt::Reduce<plus> lambda, RAJA::inclusive_scan<b200_exec>, RAJA::sort_pairs<b200_exec> "
+                                     "(bench/policy_bench.cu: the public C++ API, pools and resource included)",
+                           "cabi": "C ABI of libraja_b200.so (rb200_reduce_dot / rb200_scan / rb200_sort_pairs_buffered)"}[route]),
+                "prewarm": "0.3 s of untimed dot+scan in front of the W warm-up steps",
                 "sharding": "none" if world == 1 else ("contiguous shards; allreduce(dot), carry allgather(scan), sample-sort all-to-all(sort); exchanges by " +
                                                         ("NCCL collectives" if args.nccl_exchange else "the NVLink peer-memory communicator (sort: fused partition + all-to-all sweep)"))},
         "verified": verified["all"] if verified is not None else None, "verification": verified,
@@ -452,6 +566,8 @@ def run_b200(args):
                      "peak_source": peak_src,
                      "bytes_per_launch": n * BYTES_ONESWEEP_PASS, "avg_launch_ms": pass_ms},
         "kernels": kern,
+        "reference_gpu": reference_gpu,
+        "other_route": cabi,
         "cpu_baseline": cpu,
         "e2e": e2e,
         "gpu_launches": int(launches),
@@ -463,7 +579,7 @@ def run_b200(args):
         raise SystemExit(3)
 
 
-def run_e2e(rb, rbm, sharded, n, dev, stream, res, world, barrier, steps):
+def run_e2e(rb, rbm, sharded, paths, n, dev, stream, res, world, barrier, steps):
     """The same step through the public API from pinned HOST buffers: every step copies its inputs
     host -> device and its results device -> host inside the timed region.  Three streams (H2D, compute,
     D2H) with events between them, so the two copy engines and the kernels overlap within a step and
@@ -515,12 +631,12 @@ def run_e2e(rb, rbm, sharded, n, dev, stream, res, world, barrier, steps):
         if sharded:
             dot_t = rbm.reduce_dot(sharded, dx, dy, res=res, as_tensor=True)
         else:
-            rb._lib.check(lib.rb200_reduce_dot(rb._lib.F64, dx.data_ptr(), dy.data_ptr(), n, dot_pin.ptr, res.handle), "dot")
+            paths.dot(dx, dy)
         last["c_dot"] = ev(s_c)
         s_c.wait_event(e_s)
         if "o_scan" in last: s_c.wait_event(last["o_scan"])
         if sharded: rbm.inclusive_scan(sharded, ds, dso, res=res)
-        else: rb.inclusive_scan(ds, dso, pol=apol, res=res)
+        else: paths.scan(ds, dso)
         last["c_scan"] = ev(s_c)
         s_c.wait_event(e_kv)
         if "o_sort" in last: s_c.wait_event(last["o_sort"])  # sharded: nobody writes into a receive buffer that is still being read
@@ -528,7 +644,7 @@ def run_e2e(rb, rbm, sharded, n, dev, stream, res, world, barrier, steps):
         if sharded:
             ko, vo = rbm.sort_pairs(sharded, ku, vu, res=res, keys_alt=ka.view(torch.uint32), vals_alt=va.view(torch.uint32))
         else:
-            rb.sort_pairs(ku, vu, pol=apol, res=res, keys_alt=ka.view(torch.uint32), vals_alt=va.view(torch.uint32))
+            paths.sort_pairs(ku, vu, ka.view(torch.uint32), va.view(torch.uint32))
             ko, vo = ku, vu
         c_sort = ev(s_c)
         m = ko.numel()
@@ -552,7 +668,7 @@ def run_e2e(rb, rbm, sharded, n, dev, stream, res, world, barrier, steps):
     s_c.wait_stream(s_in); s_c.wait_stream(s_out)
     e1.record(s_c)
     barrier()
-    dot = float(ho_dot[0]) if sharded else float(dot_pin.view("float64")[0])
+    dot = float(ho_dot[0]) if sharded else paths.dot_value()
     if not dot > 0:
         raise SystemExit("bench.py: e2e dot product did not arrive on the host")
     ms = e0.elapsed_time(e1) / steps
@@ -598,6 +714,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the checked step after the timed region")
+    ap.add_argument("--route", default=None, choices=["policy", "cabi"], help="one GPU: RAJA front-ends + b200 policies (default when built) or the C ABI")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the cuda_exec / CUB arm and the other route")
     ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: exchange with NCCL collectives instead of the peer-memory communicator")
     args = ap.parse_args()
     if args.cpu_log2n is None:

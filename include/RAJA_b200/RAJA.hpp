@@ -3,10 +3,10 @@
 // Include this INSTEAD of "RAJA/RAJA.hpp" (it includes it).  It adds to an UNMODIFIED RAJA
 // (the reference, built with CUDA enabled) a new policy family
 //
-//     RAJA::b200_exec<BLOCK, Async=false>, RAJA::b200_exec_async<BLOCK>
-//     RAJA::b200_reduce                     (classic ReduceSum/Min/Max/MinLoc/MaxLoc objects)
+//     RAJA::b200_exec<BLOCK, Async=false>, RAJA::b200_exec_async<BLOCK>, RAJA::b200_exec_grid<BLOCK, GRID>
+//     RAJA::b200_reduce, b200_reduce_atomic (classic ReduceSum/Min/Max/MinLoc/MaxLoc/BitOr/BitAnd objects)
 //     RAJA::b200_multi_reduce               (MultiReduceSum/Min/Max/BitOr/BitAnd: run-time indexed bins)
-//     RAJA::b200_atomic                     (atomicAdd & friends)
+//     RAJA::b200_atomic, b200_atomic_aggregated (atomicAdd & friends)
 //     RAJA::b200_synchronize
 //     RAJA::b200_launch_t<Async>            (RAJA::launch, with or without expt::Reduce params)
 //     RAJA::b200_work<BLOCK, Async>, RAJA::unordered_b200_fused   (WorkPool / WorkGroup / WorkSite)
@@ -70,6 +70,7 @@
 #include "RAJA_b200/atomic.hpp"
 #include "RAJA_b200/scan.hpp"
 #include "RAJA_b200/sort.hpp"
+#include "RAJA_b200/indexset.hpp"
 
 // ---- 3. the reference -------------------------------------------------------------------------
 #include "RAJA/RAJA.hpp"

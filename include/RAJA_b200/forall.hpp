@@ -11,13 +11,66 @@ namespace policy
 namespace b200
 {
 
-// what param_init / param_resolve receive (the reference hands its cudaInfo: MemUtils_CUDA.hpp:380-394)
+// what param_init / param_resolve receive (the reference hands its cudaInfo: MemUtils_CUDA.hpp:380-394).
+// Besides the launch shape it collects the device addresses of the reducer results of ONE launch, so that
+// param_resolve fetches them all with one batch of copies into one pinned block and ONE stream wait -- the
+// reference waits once per reducer (policy/cuda/params/reduce.hpp:46-60).
 struct LaunchInfo
 {
   int grid;
   int block;
   cudaStream_t stream;
   RAJA::resources::Cuda res;
+
+  static constexpr int max_results = 16;
+  struct Result
+  {
+    const void* dev;
+    unsigned bytes, offset;
+  };
+  Result results[max_results] = {};
+  int n_results    = 0;
+  unsigned staged  = 0;        // bytes of the pinned block in use
+  void* staging    = nullptr;  // pinned block, filled at the first fetch
+  bool fetched     = false;
+
+  // param_init: a result of `bytes` bytes will appear at device address `dev`
+  void expect(const void* dev, size_t bytes)
+  {
+    if (n_results < max_results)
+    {
+      results[n_results++] = Result {dev, (unsigned)bytes, staged};
+      staged += (unsigned)((bytes + 15) & ~size_t(15));
+    }
+  }
+  // param_resolve: host copy of the result at `dev` (valid until this LaunchInfo is destroyed)
+  const void* fetch(const void* dev, size_t bytes)
+  {
+    if (!fetched && n_results > 0)
+    {
+      staging = rb200_pinned_malloc(staged);
+      if (!staging) throw std::runtime_error(std::string("raja_b200: reducer staging: ") + rb200_last_error());
+      for (int i = 0; i < n_results; ++i)
+        RAJA::b200_detail::check(cudaMemcpyAsync(static_cast<char*>(staging) + results[i].offset, results[i].dev, results[i].bytes,
+                                                 cudaMemcpyDeviceToHost, stream),
+                                 "reducer readback");
+      RAJA::b200_detail::check(cudaStreamSynchronize(stream), "reducer readback");
+      fetched = true;
+    }
+    for (int i = 0; i < n_results; ++i)
+      if (results[i].dev == dev) return static_cast<char*>(staging) + results[i].offset;
+    // more reducers than slots: fetch this one on its own
+    if (!overflow) overflow = rb200_pinned_malloc(64);
+    RAJA::b200_detail::check(cudaMemcpyAsync(overflow, dev, bytes, cudaMemcpyDeviceToHost, stream), "reducer readback");
+    RAJA::b200_detail::check(cudaStreamSynchronize(stream), "reducer readback");
+    return overflow;
+  }
+  ~LaunchInfo()
+  {
+    if (staging) rb200_pinned_free(staging);
+    if (overflow) rb200_pinned_free(overflow);
+  }
+  void* overflow = nullptr;
 };
 
 namespace detail
@@ -51,14 +104,14 @@ struct Finalize
 };
 }  // namespace detail
 
-template<typename Iterable, typename LoopBody, size_t BLOCK_SIZE, bool Async, typename ForallParam>
+template<typename Iterable, typename LoopBody, size_t BLOCK_SIZE, size_t GRID_SIZE, bool Async, typename ForallParam>
 RAJA_INLINE concepts::enable_if_t<resources::EventProxy<resources::Cuda>, RAJA::expt::type_traits::is_ForallParamPack<ForallParam>>
-forall_impl(resources::Cuda res, b200_exec<BLOCK_SIZE, Async> const& pol, Iterable&& iter, LoopBody&& loop_body, ForallParam f_params)
+forall_impl(resources::Cuda res, b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async> const& pol, Iterable&& iter, LoopBody&& loop_body, ForallParam f_params)
 {
   using Iterator  = camp::decay<decltype(std::begin(iter))>;
   using LOOP_BODY = camp::decay<LoopBody>;
   using IndexType = camp::decay<decltype(std::distance(std::begin(iter), std::end(iter)))>;
-  using EXEC_POL  = b200_exec<BLOCK_SIZE, Async>;
+  using EXEC_POL  = b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async>;
   using BodyT     = detail::Body<LOOP_BODY, Iterator, camp::decay<ForallParam>>;
   using FinT      = detail::Finalize<EXEC_POL, camp::decay<ForallParam>>;
   constexpr int UNROLL = 4;
@@ -72,7 +125,9 @@ forall_impl(resources::Cuda res, b200_exec<BLOCK_SIZE, Async> const& pol, Iterab
   if (len > 0)
   {
     cudaStream_t stream = res.get_stream();
-    LaunchInfo info {::b200::forall_grid<(int)BLOCK_SIZE, UNROLL, IndexType, BodyT, FinT>(len), (int)BLOCK_SIZE, stream, res};
+    // b200_exec_grid<BLOCK, GRID>: the caller's grid (never more blocks than units of work); otherwise SMs x resident CTAs
+    int grid = ::b200::forall_grid<(int)BLOCK_SIZE, UNROLL, IndexType, BodyT, FinT>(len, (long long)GRID_SIZE);
+    LaunchInfo info {grid, (int)BLOCK_SIZE, stream, res};
     if constexpr (!empty) RAJA::expt::ParamMultiplexer::parampack_init(pol, f_params, info);
     {
       // classic reducer objects captured by the body set themselves up for this launch when the body
@@ -96,7 +151,12 @@ forall_impl(resources::Cuda res, b200_exec<BLOCK_SIZE, Async> const& pol, Iterab
 }
 
 // RAJA::synchronize<b200_synchronize>() (policy/cuda/synchronize.hpp:39-42)
-RAJA_INLINE void synchronize_impl(const b200_synchronize&) { RAJA::b200_detail::check(cudaDeviceSynchronize(), "synchronize"); }
+// waits for the streams the back-end has launched on since they were last waited for, not for the whole device
+// (RAJA::cuda::synchronize(), policy/cuda/MemUtils_CUDA.hpp:207-231)
+RAJA_INLINE void synchronize_impl(const b200_synchronize&)
+{
+  if (rb200_synchronize_streams() < 0) throw std::runtime_error(std::string("raja_b200: synchronize: ") + rb200_last_error());
+}
 
 }  // namespace b200
 }  // namespace policy
@@ -106,8 +166,8 @@ namespace resources
 // TypedIndexSet foralls (ExecPolicy<seq_segit, b200_exec<...>>) run on a Cuda resource; the per-segment
 // dispatch is the generic one (pattern/forall.hpp:279-299 -> CallForall -> ADL forall_impl above).
 // Mirrors util/resource.hpp:95-113.
-template<typename ISetIter, size_t BLOCK_SIZE, bool Async>
-struct get_resource<ExecPolicy<ISetIter, ::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async>>>
+template<typename ISetIter, size_t BLOCK_SIZE, size_t GRID_SIZE, bool Async>
+struct get_resource<ExecPolicy<ISetIter, ::RAJA::policy::b200::b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async>>>
 {
   using type = camp::resources::Cuda;
 };

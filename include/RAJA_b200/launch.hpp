@@ -42,77 +42,13 @@ struct get_resource<::RAJA::policy::b200::b200_launch_t<Async>>
 
 namespace b200_detail
 {
-// Block + grid combine of one value per thread for a launch of ANY shape.  slot[0] receives the result,
-// slot[1 ..] the per-team partials; `counter` is a zeroed, self-resetting ticket (atomicInc wraps).
-// Fold order is fixed: lanes ascending inside a warp, warps ascending inside a team, teams ascending.
+// Block + grid combine of one value per thread for a launch of ANY shape (shaped_grid_reduce, RAJA_b200/reduce.hpp).
+// slot[0] receives the result, slot[1 ..] the per-team partials; `counter` is a zeroed, self-resetting ticket.
 template<class Op>
 __device__ __forceinline__ void launch_grid_reduce_to_slot(typename Op::value_type v, typename Op::value_type* slot, unsigned* counter)
 {
-  using T = typename Op::value_type;
-  __shared__ alignas(16) unsigned char raw[32 * sizeof(T)];
-  __shared__ bool s_last;
-  T* smem = reinterpret_cast<T*>(raw);
-  Op op;
-  const unsigned nthreads = blockDim.x * blockDim.y * blockDim.z;
-  const unsigned tid      = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
-  const unsigned nblocks  = gridDim.x * gridDim.y * gridDim.z;
-  const unsigned bid      = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-  const unsigned lane = tid & 31u, w = tid >> 5, nw = (nthreads + 31u) >> 5;
-
-  // ordered tree over the lanes that exist in this warp (the last warp of a team may be partial)
-  auto warp_fold = [&](T x, unsigned count) {
-    const unsigned mask = count >= 32u ? 0xffffffffu : ((1u << count) - 1u);
-#pragma unroll
-    for (unsigned m = 1; m < 32u; m <<= 1)
-    {
-      T o = ::b200::shfl_idx_mask(mask, x, (int)((lane + m) < count ? lane + m : lane));
-      if (lane + m < count && (lane & (2u * m - 1u)) == 0u) x = op(x, o);
-    }
-    return x;  // valid in lane 0
-  };
-  const unsigned in_warp = (nthreads - w * 32u) < 32u ? (nthreads - w * 32u) : 32u;
-  v = warp_fold(v, in_warp);
-  if (lane == 0) smem[w] = v;
-  __syncthreads();
-  if (w == 0)
-  {
-    if (nw > 1)  // then warp 0 is a full warp
-    {
-      v = (lane < nw) ? smem[lane] : Op::identity();
-      v = warp_fold(v, 32u);
-    }
-    if (lane == 0)
-    {
-      ::b200::st_cg(slot + 1 + bid, v);
-      __threadfence();
-      const unsigned ticket = ::atomicInc(counter, nblocks - 1u);
-      s_last = (ticket == nblocks - 1u);
-    }
-  }
-  __syncthreads();
-  if (s_last)
-  {
-    __threadfence();
-    // every thread folds a CONTIGUOUS range of partials, so the final order is team order
-    const unsigned per = (nblocks + nthreads - 1u) / nthreads;
-    const unsigned lo = tid * per, hi = (lo + per < nblocks) ? lo + per : nblocks;
-    T acc = Op::identity();
-    for (unsigned i = lo; i < hi; ++i) acc = op(acc, ::b200::ld_cg(slot + 1 + i));
-    acc = warp_fold(acc, in_warp);
-    __syncthreads();  // smem reuse
-    if (lane == 0) smem[w] = acc;
-    __syncthreads();
-    if (w == 0)
-    {
-      if (nw > 1)
-      {
-        acc = (lane < nw) ? smem[lane] : Op::identity();
-        acc = warp_fold(acc, 32u);
-      }
-      if (lane == 0) ::b200::st_cg(slot, acc);
-    }
-  }
-  __syncthreads();  // smem and s_last are reused by the next reducer of the pack
+  typename Op::value_type r;
+  if (shaped_grid_reduce<Op>(v, slot + 1, counter, r)) ::b200::st_cg(slot, r);
 }
 }  // namespace b200_detail
 
@@ -126,6 +62,7 @@ inline void param_init(::RAJA::policy::b200::b200_launch_t<Async> const&, Reduce
   red.devicetarget = static_cast<T*>(rb200_device_malloc(sizeof(T) * ((size_t)li.grid + 1), li.stream));
   red.device_count = static_cast<unsigned int*>(rb200_device_zeroed_malloc(sizeof(unsigned int), li.stream));
   if (!red.devicetarget || !red.device_count) throw std::runtime_error(std::string("raja_b200: reducer scratch: ") + rb200_last_error());
+  li.expect(red.devicetarget, sizeof(T));
 }
 
 template<bool Async, typename OP, typename T, typename VOp>
@@ -142,27 +79,22 @@ RAJA_HOST_DEVICE inline void param_combine(::RAJA::policy::b200::b200_launch_t<A
 template<bool Async, typename OP, typename T, typename VOp>
 inline void param_resolve(::RAJA::policy::b200::b200_launch_t<Async> const&, Reducer<OP, T, VOp>& red, ::RAJA::policy::b200::LaunchInfo& li)
 {
-  // folded into the user's target on the host, as the reference does after res.wait() (policy/cuda/params/reduce.hpp:46-60)
-  alignas(alignof(T)) unsigned char raw[sizeof(T)];
-  ::RAJA::b200_detail::check(cudaMemcpyAsync(raw, red.devicetarget, sizeof(T), cudaMemcpyDeviceToHost, li.stream), "reducer readback");
-  ::RAJA::b200_detail::check(cudaStreamSynchronize(li.stream), "reducer readback");
-  T value = *reinterpret_cast<T*>(raw);
-  red.combineTarget(value);
-  rb200_device_zeroed_free(red.device_count, li.stream);
-  red.device_count = nullptr;
-  rb200_device_free(red.devicetarget, li.stream);
-  red.devicetarget = nullptr;
+  b200_resolve::resolve(red, li);
 }
 
 template<bool Async>
-inline void param_init(::RAJA::policy::b200::b200_launch_t<Async> const&, RAJA::detail::Name&, const ::RAJA::policy::b200::LaunchInfo&)
-{}
+inline void param_init(::RAJA::policy::b200::b200_launch_t<Async> const&, RAJA::detail::Name& kn, const ::RAJA::policy::b200::LaunchInfo&)
+{
+  if (kn.name != nullptr) rb200_range_push(kn.name);
+}
 template<bool Async>
 RAJA_HOST_DEVICE inline void param_combine(::RAJA::policy::b200::b200_launch_t<Async> const&, RAJA::detail::Name&)
 {}
 template<bool Async>
-inline void param_resolve(::RAJA::policy::b200::b200_launch_t<Async> const&, RAJA::detail::Name&, const ::RAJA::policy::b200::LaunchInfo&)
-{}
+inline void param_resolve(::RAJA::policy::b200::b200_launch_t<Async> const&, RAJA::detail::Name& kn, const ::RAJA::policy::b200::LaunchInfo&)
+{
+  if (kn.name != nullptr) rb200_range_pop();
+}
 }  // namespace detail
 }  // namespace expt
 
@@ -221,10 +153,22 @@ struct LaunchExecute<::RAJA::policy::b200::b200_launch_t<async>>
       auto kern = &b200_detail::launch_kernel<BODY>;
       if (params.shared_mem_size > 48 * 1024)
         b200_detail::check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)params.shared_mem_size), "launch shared memory");
-      BODY body = body_in;
-      kern<<<grid, block, params.shared_mem_size, stream>>>(body);
+      // classic reducer objects captured by the body set themselves up for this launch while the body is copied
+      auto make_body = [&]() {
+        b200_detail::LaunchScope scope((int)(grid.x * grid.y * grid.z), stream);
+        return BODY(body_in);
+      };
+      BODY body = make_body();
+      {
+        ::b200::LaunchScope hook("launch_kernel", stream);
+        kern<<<grid, block, params.shared_mem_size, stream>>>(body);
+      }
       b200_detail::check(cudaGetLastError(), "launch");
-      if (!async) cuda_res.wait();
+      if (!async)
+      {
+        cuda_res.wait();
+        rb200_stream_mark_synced(stream);
+      }
     }
     return resources::EventProxy<resources::Resource>(res);
   }
@@ -248,11 +192,22 @@ struct LaunchExecute<::RAJA::policy::b200::b200_launch_t<async>>
         b200_detail::check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)params.shared_mem_size), "launch shared memory");
       ::RAJA::policy::b200::LaunchInfo info {(int)(grid.x * grid.y * grid.z), (int)(block.x * block.y * block.z), stream, cuda_res};
       RAJA::expt::ParamMultiplexer::parampack_init(POL {}, launch_reducers, info);
-      BODY body = body_in;
-      kern<<<grid, block, params.shared_mem_size, stream>>>(body, launch_reducers);
+      auto make_body = [&]() {
+        b200_detail::LaunchScope scope(info.grid, stream);
+        return BODY(body_in);
+      };
+      BODY body = make_body();
+      {
+        ::b200::LaunchScope hook("launch_reduce_kernel", stream);
+        kern<<<grid, block, params.shared_mem_size, stream>>>(body, launch_reducers);
+      }
       b200_detail::check(cudaGetLastError(), "launch");
       RAJA::expt::ParamMultiplexer::parampack_resolve(POL {}, launch_reducers, info);
-      if (!async) cuda_res.wait();
+      if (!async)
+      {
+        cuda_res.wait();
+        rb200_stream_mark_synced(stream);
+      }
     }
     return resources::EventProxy<resources::Resource>(res);
   }

@@ -16,8 +16,11 @@ constexpr ::RAJA::Policy policy_id = static_cast<::RAJA::Policy>(64);
 
 // One mapping: a persistent grid (SMs x resident CTAs) walking BLOCK*UNROLL tiles.  The reference's
 // Direct / StridedLoop / occupancy-calculator variants (policy/cuda/policy.hpp:1257-1322) collapse to it.
-template<size_t BLOCK_SIZE, bool Async = false>
-struct b200_exec
+// GRID_SIZE == 0: the grid is sized from the occupancy of the instantiated kernel (SMs x resident CTAs, never more
+// blocks than tiles); GRID_SIZE > 0 fixes it (cuda_exec_grid, policy/cuda/policy.hpp:1276-1290) -- the persistent
+// kernel walks its tiles round-robin with whatever grid it is given.
+template<size_t BLOCK_SIZE, size_t GRID_SIZE, bool Async = false>
+struct b200_exec_explicit
     : public RAJA::make_policy_pattern_launch_platform_t<policy_id,
                                                          RAJA::Pattern::forall,
                                                          (Async ? RAJA::Launch::async : RAJA::Launch::sync),
@@ -25,13 +28,26 @@ struct b200_exec
 {
   static_assert(BLOCK_SIZE % 32 == 0 && BLOCK_SIZE >= 32 && BLOCK_SIZE <= 1024, "BLOCK_SIZE must be a multiple of 32, at most 1024");
   static constexpr size_t block_size = BLOCK_SIZE;
+  static constexpr size_t grid_size  = GRID_SIZE;
   static constexpr bool async        = Async;
 };
+template<size_t BLOCK_SIZE, bool Async = false>
+using b200_exec = b200_exec_explicit<BLOCK_SIZE, 0, Async>;
 
-// classic reducer objects (policy/cuda/policy.hpp:1610-1620).  Deterministic: fixed slot order.
-struct b200_reduce
+// classic reducer objects (policy/cuda/policy.hpp:1550-1620).  Ordered: last-block-done over the grid's partials in fixed
+// slot order (run-to-run deterministic).  Unordered ("atomic"): one device atomic per block on a self-resetting slot;
+// value types / operators the ISA has no atomic for fall back to the ordered combine, as the reference's atomic
+// tunings do (policy/cuda/reduce.hpp:1001-1030).
+template<bool Ordered>
+struct b200_reduce_policy
     : public RAJA::make_policy_pattern_launch_platform_t<policy_id, RAJA::Pattern::reduce, RAJA::Launch::undefined, RAJA::Platform::cuda>
-{};
+{
+  static constexpr bool ordered = Ordered;
+};
+using b200_reduce        = b200_reduce_policy<true>;
+using b200_reduce_atomic = b200_reduce_policy<false>;
+template<bool with_atomic>
+using b200_reduce_base = std::conditional_t<with_atomic, b200_reduce_atomic, b200_reduce>;
 
 // atomics: device code uses hardware atomics, host code falls through to host_policy
 // (policy/cuda/policy.hpp:437-445, policy/cuda/atomic.hpp:690-700)
@@ -50,16 +66,24 @@ struct b200_synchronize
 using policy::b200::b200_atomic;
 using policy::b200::b200_atomic_explicit;
 using policy::b200::b200_exec;
+using policy::b200::b200_exec_explicit;
 using policy::b200::b200_reduce;
+using policy::b200::b200_reduce_atomic;
+using policy::b200::b200_reduce_base;
+using policy::b200::b200_reduce_policy;
 using policy::b200::b200_synchronize;
 template<size_t BLOCK_SIZE>
-using b200_exec_async = policy::b200::b200_exec<BLOCK_SIZE, true>;
+using b200_exec_async = policy::b200::b200_exec_explicit<BLOCK_SIZE, 0, true>;
+template<size_t BLOCK_SIZE, size_t GRID_SIZE>
+using b200_exec_grid = policy::b200::b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, false>;
+template<size_t BLOCK_SIZE, size_t GRID_SIZE>
+using b200_exec_grid_async = policy::b200::b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, true>;
 
 namespace resources
 {
 // primary template: util/resource.hpp:44-48; CUDA specialisations: 72-113
-template<size_t BLOCK_SIZE, bool Async>
-struct get_resource<::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async>>
+template<size_t BLOCK_SIZE, size_t GRID_SIZE, bool Async>
+struct get_resource<::RAJA::policy::b200::b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async>>
 {
   using type = camp::resources::Cuda;
 };

@@ -1,24 +1,31 @@
 // Classic reducer objects for the b200 back-end: ReduceSum / ReduceMin / ReduceMax / ReduceMinLoc /
-// ReduceMaxLoc / ReduceBitOr / ReduceBitAnd <RAJA::b200_reduce, T[, IndexType]>.
+// ReduceMaxLoc / ReduceBitOr / ReduceBitAnd <RAJA::b200_reduce | RAJA::b200_reduce_atomic, T[, IndexType]>.
 // Replaces policy/cuda/reduce.hpp:968-1378 (cuda::Reduce, its data classes :678-965 and PinnedTally :474-661).
 //
-// Protocol (same idea as the reference, much less machinery):
-//   ROOT     the object the user declared.  Owns a control block with one pinned, device-visible tally.
-//   LAUNCH   the copy made while forall_impl copies the loop body for a launch (the launch record of
-//            RAJA_b200/policy.hpp is active): takes per-launch scratch -- one partial per block of the
-//            persistent grid and a self-resetting counter -- from the stream-ordered pools, and returns
-//            it when it is destroyed (safe right after enqueue).
+// Protocol (same object model as the reference, much less machinery):
+//   ROOT     the object the user declared.  Owns a control block: the streams that have launches of this reducer
+//            in flight and a growing list of pinned, device-visible result slots, ONE PER LAUNCH (the role of
+//            PinnedTally's per-stream value nodes) -- launches on different, unordered streams never touch the
+//            same slot, so sharing one reducer between streams is safe.
+//   LAUNCH   the copy made while a launch copies its loop body (the launch record of RAJA_b200/policy.hpp is
+//            active): takes a result slot and per-launch scratch from the stream-ordered pools -- ordered policy:
+//            one partial per block + a self-resetting counter; atomic policy: 16 zeroed bytes (counter + a
+//            self-resetting atomic slot, b200/reduce.cuh) -- and returns the scratch when it is destroyed (safe
+//            right after enqueue).
 //   ALIAS    any further host copy of a LAUNCH copy (the by-value kernel argument): just carries pointers.
-//   HOST     any other host copy: starts at the identity, folds into its parent on destruction.
-//   device   every thread's private copy (made by the engine, b200/forall.cuh): starts at the identity;
-//            its destructor runs the block reduce and the last-block-done grid combine, and the last
-//            block folds the launch's result into the pinned tally.
-// get() waits for the streams that were used, folds the tally into the host value and returns it.
-// One reducer may be used in launches on several streams only if those launches are ordered
-// (the tally is one slot, not the reference's per-stream list).
+//   HOST     any other host copy: starts at the identity, folds into the object it was copied from on destruction.
+//   DEVICE   copies made in device code.  A copy OF THE KERNEL ARGUMENT (every thread's private copy, made by the
+//            engine) runs the block + grid combine in its destructor and the last block stores the launch's result
+//            into the slot; a copy of a device copy (a by-value re-capture inside the loop body) folds into the copy
+//            it was made from (policy/cuda/reduce.hpp:1109-1118: `if (!parent->parent) grid_reduce else combine`).
+// get() waits for the streams that were used, folds the slots into the host value in launch order and returns it.
+// Block shapes are read at run time (1-3 D, partial last warp allowed), so the same objects work inside
+// RAJA::forall, RAJA::launch and RAJA::kernel launches of this back-end.
 #ifndef RAJA_B200_REDUCE_CLASSIC_HPP
 #define RAJA_B200_REDUCE_CLASSIC_HPP
 
+#include <mutex>
+#include <new>
 #include <vector>
 
 namespace RAJA
@@ -28,73 +35,57 @@ namespace b200
 namespace detail
 {
 
-// block reduce for a block size only known at run time (a destructor has no policy to read it from)
-template<class Op>
-__device__ __forceinline__ typename Op::value_type block_reduce_rt(typename Op::value_type v, Op op, typename Op::value_type* smem)
-{
-  using T = typename Op::value_type;
-  v = ::b200::warp_allreduce(v, op);
-  const int nw = (blockDim.x + 31) >> 5;
-  if (nw == 1) return v;
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) smem[w] = v;
-  __syncthreads();
-  if (w == 0)
-  {
-    v = (l < nw) ? smem[l] : Op::identity();
-    v = ::b200::warp_allreduce(v, op);
-  }
-  return v;
-}
-
-template<class Op>
+template<class Op, bool Ordered = true>
 class Reduce
 {
 public:
   using T = typename Op::value_type;
+  // operators / value types without a hardware atomic fall back to the ordered combine
+  static constexpr bool use_atomic = !Ordered && ::b200::AtomicSlot<Op>::available;
 
   Reduce() : Reduce(T(), Op::identity()) {}
 
   explicit Reduce(T init_val, T identity_ = Op::identity())
-      : m_parent(this), m_ctl(new Control), m_value(init_val), m_identity(identity_), m_partials(nullptr), m_counter(nullptr), m_kind(ROOT)
-  {
-    m_tally = static_cast<T*>(rb200_pinned_malloc(sizeof(T)));  // mapped pinned memory: one address for host and device
-    if (!m_tally) throw std::runtime_error(std::string("raja_b200: reducer tally: ") + rb200_last_error());
-    *m_tally = m_identity;
-  }
+      : m_parent(this), m_ctl(new Control), m_value(init_val), m_identity(identity_), m_scratch(nullptr), m_counter(nullptr), m_out(nullptr), m_kind(ROOT)
+  {}
 
   void reset(T in_val, T identity_ = Op::identity())
   {
     (void)get();  // syncs outstanding launches
     m_value    = in_val;
     m_identity = identity_;
-    *m_tally   = m_identity;
   }
 
   RAJA_HOST_DEVICE Reduce(const Reduce& other)
-      : m_parent(other.m_parent), m_ctl(other.m_ctl), m_value(other.m_identity), m_identity(other.m_identity), m_partials(other.m_partials),
-        m_counter(other.m_counter), m_kind(HOST), m_stream(other.m_stream), m_tally(other.m_tally)
+      : m_parent(&other), m_ctl(other.m_ctl), m_value(other.m_identity), m_identity(other.m_identity), m_scratch(other.m_scratch),
+        m_counter(other.m_counter), m_out(other.m_out), m_kind(HOST), m_stream(other.m_stream)
   {
 #if !defined(__CUDA_ARCH__)
     if (other.m_kind == LAUNCH || other.m_kind == ALIAS)
     {
-      m_kind = ALIAS;
+      m_kind   = ALIAS;
+      m_parent = nullptr;
     }
     else
     {
       ::RAJA::b200_detail::LaunchRecord& lr = ::RAJA::b200_detail::tl_launch();
       if (lr.active)
       {
-        m_kind     = LAUNCH;
-        m_stream   = lr.stream;
-        m_partials = static_cast<T*>(rb200_device_malloc(sizeof(T) * (size_t)lr.grid, lr.stream));
-        m_counter  = static_cast<unsigned*>(rb200_device_zeroed_malloc(sizeof(unsigned), lr.stream));
-        if (!m_partials || !m_counter) throw std::runtime_error(std::string("raja_b200: reducer scratch: ") + rb200_last_error());
-        m_ctl->note_stream(lr.stream);
-      }
-      else if (other.m_kind == ROOT || other.m_kind == HOST)
-      {
-        m_parent = &other;  // fold into the object this was copied from
+        m_kind   = LAUNCH;
+        m_parent = nullptr;
+        m_stream = lr.stream;
+        if (use_atomic)
+        {
+          m_counter = static_cast<unsigned*>(rb200_device_zeroed_malloc(16, lr.stream));
+          m_scratch = nullptr;
+        }
+        else
+        {
+          m_scratch = static_cast<T*>(rb200_device_malloc(sizeof(T) * (size_t)lr.grid, lr.stream));
+          m_counter = static_cast<unsigned*>(rb200_device_zeroed_malloc(sizeof(unsigned), lr.stream));
+        }
+        if (!m_counter || (!use_atomic && !m_scratch)) throw std::runtime_error(std::string("raja_b200: reducer scratch: ") + rb200_last_error());
+        m_out = m_ctl->new_slot(lr.stream, m_identity);
       }
     }
 #else
@@ -109,61 +100,52 @@ public:
 #if !defined(__CUDA_ARCH__)
     switch (m_kind)
     {
-      case ROOT:
-        if (m_tally) rb200_pinned_free(m_tally);
-        delete m_ctl;
-        break;
+      case ROOT: delete m_ctl; break;
       case LAUNCH:
-        rb200_device_free(m_partials, m_stream);
+        if (m_scratch) rb200_device_free(m_scratch, m_stream);
         rb200_device_zeroed_free(m_counter, m_stream);
         break;
       case HOST:
-        if (m_parent && m_parent != this) m_parent->combine(m_value);
+        if (m_parent && m_parent != this)
+        {
+          std::lock_guard<std::mutex> lock(m_ctl->mu);
+          m_parent->combine(m_value);
+        }
         break;
       default: break;
     }
 #else
-    // every thread of the block gets here (the engine's private copy goes out of scope once per thread)
-    __shared__ alignas(16) unsigned char raw[32 * sizeof(T)];
-    T* smem = reinterpret_cast<T*>(raw);
-    Op op;
-    T v = block_reduce_rt(m_value, op, smem);
-    __shared__ bool s_last;
-    if (threadIdx.x == 0)
+    if (m_kind != DEVICE || m_parent == nullptr) return;
+    const Kind from = m_parent->m_kind;
+    if (from == DEVICE)
     {
-      ::b200::st_cg(m_partials + blockIdx.x, v);
-      __threadfence();
-      const unsigned ticket = ::atomicInc(m_counter, gridDim.x - 1);  // wraps back to 0: scratch is returned zeroed
-      s_last                = (ticket == gridDim.x - 1);
+      m_parent->combine(m_value);  // a re-capture inside the loop body: same thread, no synchronisation
     }
-    __syncthreads();
-    if (s_last)
+    else if ((from == LAUNCH || from == ALIAS) && m_counter != nullptr)
     {
-      __threadfence();
-      T acc = Op::identity();
-      for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) acc = op(acc, ::b200::ld_cg(m_partials + i));
-      __syncthreads();
-      acc = block_reduce_rt(acc, op, smem);
-      if (threadIdx.x == 0)
-      {
-        *m_tally = op(*m_tally, acc);  // launches that share a reducer are stream-ordered
-      }
+      // every thread of the block gets here (the engine's private copy goes out of scope once per thread)
+      T r;
+      bool mine;
+      if constexpr (use_atomic) mine = ::RAJA::b200_detail::shaped_grid_reduce_atomic<Op>(m_value, m_counter, r);
+      else mine = ::RAJA::b200_detail::shaped_grid_reduce<Op>(m_value, m_scratch, m_counter, r);
+      if (mine) *m_out = r;  // this launch's own pinned slot
     }
-    __syncthreads();
+    // else: copied into a kernel without a launch record of this back-end -- nothing to combine into
 #endif
   }
 
-  //! synchronises the streams this reducer was used on, folds the device tally in, returns the value
+  //! synchronises the streams this reducer was used on, folds the launches' results in, returns the value
   T get()
   {
     Control* c = m_ctl;
-    if (!c->streams.empty())
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (c->used > 0)
     {
       for (cudaStream_t s : c->streams) ::RAJA::b200_detail::check(cudaStreamSynchronize(s), "reducer get");
       c->streams.clear();
       Op op;
-      m_value  = op(m_value, *m_tally);
-      *m_tally = m_identity;
+      for (size_t i = 0; i < c->used; ++i) m_value = op(m_value, *c->slot(i));
+      c->used = 0;
     }
     return m_value;
   }
@@ -175,25 +157,44 @@ public:
 
 private:
   enum Kind : int { ROOT, HOST, LAUNCH, ALIAS, DEVICE };
-  struct Control  // shared by the root and its copies: which streams have launches in flight
+  struct Control  // shared by the root and its host copies
   {
-    std::vector<cudaStream_t> streams;
-    void note_stream(cudaStream_t s)
+    static constexpr size_t chunk = 64;
+    std::mutex mu;
+    std::vector<cudaStream_t> streams;  // streams with launches in flight since the last get()
+    std::vector<T*> chunks;             // pinned, device-visible slots, `chunk` per allocation
+    size_t used = 0;                    // slots handed out since the last get()
+    T* slot(size_t i) { return chunks[i / chunk] + (i % chunk); }
+    T* new_slot(cudaStream_t s, const T& identity)
     {
-      for (cudaStream_t t : streams)
-        if (t == s) return;
-      streams.push_back(s);
+      std::lock_guard<std::mutex> lock(mu);
+      bool seen = false;
+      for (cudaStream_t t : streams) seen = seen || (t == s);
+      if (!seen) streams.push_back(s);
+      if (used / chunk >= chunks.size())
+      {
+        T* p = static_cast<T*>(rb200_pinned_malloc(sizeof(T) * chunk));  // mapped pinned memory: one address for host and device
+        if (!p) throw std::runtime_error(std::string("raja_b200: reducer tally: ") + rb200_last_error());
+        chunks.push_back(p);
+      }
+      T* p = slot(used++);
+      new (p) T(identity);  // a launch whose grid never runs (error) contributes nothing
+      return p;
+    }
+    ~Control()
+    {
+      for (T* p : chunks) rb200_pinned_free(p);
     }
   };
   const Reduce* m_parent;
   Control* m_ctl;
   mutable T m_value;
   T m_identity;
-  T* m_partials;
-  unsigned* m_counter;
+  T* m_scratch;         // ordered: one partial per block
+  unsigned* m_counter;  // zeroed, self-resetting ticket (atomic policy: 16 bytes, ticket + slot)
+  T* m_out;             // pinned result slot of this launch
   Kind m_kind;
   cudaStream_t m_stream = 0;
-  T* m_tally            = nullptr;  // pinned, device-visible running result of the launches so far
 };
 
 }  // namespace detail
@@ -225,26 +226,14 @@ struct ValueLocOp
     return take_b ? b : a;
   }
 };
-template<class T> struct BitOrOp
-{
-  using value_type = T;
-  RAJA_HOST_DEVICE static T identity() { return T(0); }
-  RAJA_HOST_DEVICE T operator()(T a, T b) const { return a | b; }
-};
-template<class T> struct BitAndOp
-{
-  using value_type = T;
-  RAJA_HOST_DEVICE static T identity() { return ~T(0); }
-  RAJA_HOST_DEVICE T operator()(T a, T b) const { return a & b; }
-};
 }  // namespace b200_detail
 
 // ---- the specialisations user code names (primary templates: pattern/reduce.hpp:80-233) -----------------
-template<typename T>
-class ReduceSum<b200_reduce, T> : public b200::detail::Reduce<::b200::Plus<T>>
+template<bool Ordered, typename T>
+class ReduceSum<b200_reduce_policy<Ordered>, T> : public b200::detail::Reduce<::b200::Plus<T>, Ordered>
 {
 public:
-  using Base = b200::detail::Reduce<::b200::Plus<T>>;
+  using Base = b200::detail::Reduce<::b200::Plus<T>, Ordered>;
   using Base::Base;
   RAJA_HOST_DEVICE const ReduceSum& operator+=(T rhs) const
   {
@@ -252,11 +241,11 @@ public:
     return *this;
   }
 };
-template<typename T>
-class ReduceMin<b200_reduce, T> : public b200::detail::Reduce<::b200::Minimum<T>>
+template<bool Ordered, typename T>
+class ReduceMin<b200_reduce_policy<Ordered>, T> : public b200::detail::Reduce<::b200::Minimum<T>, Ordered>
 {
 public:
-  using Base = b200::detail::Reduce<::b200::Minimum<T>>;
+  using Base = b200::detail::Reduce<::b200::Minimum<T>, Ordered>;
   using Base::Base;
   RAJA_HOST_DEVICE const ReduceMin& min(T rhs) const
   {
@@ -264,11 +253,11 @@ public:
     return *this;
   }
 };
-template<typename T>
-class ReduceMax<b200_reduce, T> : public b200::detail::Reduce<::b200::Maximum<T>>
+template<bool Ordered, typename T>
+class ReduceMax<b200_reduce_policy<Ordered>, T> : public b200::detail::Reduce<::b200::Maximum<T>, Ordered>
 {
 public:
-  using Base = b200::detail::Reduce<::b200::Maximum<T>>;
+  using Base = b200::detail::Reduce<::b200::Maximum<T>, Ordered>;
   using Base::Base;
   RAJA_HOST_DEVICE const ReduceMax& max(T rhs) const
   {
@@ -276,11 +265,11 @@ public:
     return *this;
   }
 };
-template<typename T>
-class ReduceBitOr<b200_reduce, T> : public b200::detail::Reduce<b200_detail::BitOrOp<T>>
+template<bool Ordered, typename T>
+class ReduceBitOr<b200_reduce_policy<Ordered>, T> : public b200::detail::Reduce<::b200::BitOr<T>, Ordered>
 {
 public:
-  using Base = b200::detail::Reduce<b200_detail::BitOrOp<T>>;
+  using Base = b200::detail::Reduce<::b200::BitOr<T>, Ordered>;
   using Base::Base;
   RAJA_HOST_DEVICE const ReduceBitOr& operator|=(T rhs) const
   {
@@ -288,11 +277,11 @@ public:
     return *this;
   }
 };
-template<typename T>
-class ReduceBitAnd<b200_reduce, T> : public b200::detail::Reduce<b200_detail::BitAndOp<T>>
+template<bool Ordered, typename T>
+class ReduceBitAnd<b200_reduce_policy<Ordered>, T> : public b200::detail::Reduce<::b200::BitAnd<T>, Ordered>
 {
 public:
-  using Base = b200::detail::Reduce<b200_detail::BitAndOp<T>>;
+  using Base = b200::detail::Reduce<::b200::BitAnd<T>, Ordered>;
   using Base::Base;
   RAJA_HOST_DEVICE const ReduceBitAnd& operator&=(T rhs) const
   {
@@ -300,13 +289,15 @@ public:
     return *this;
   }
 };
-template<typename T, typename IndexType>
-class ReduceMinLoc<b200_reduce, T, IndexType> : public b200::detail::Reduce<b200_detail::ValueLocOp<T, IndexType, true>>
+template<bool Ordered, typename T, typename IndexType>
+class ReduceMinLoc<b200_reduce_policy<Ordered>, T, IndexType> : public b200::detail::Reduce<b200_detail::ValueLocOp<T, IndexType, true>, Ordered>
 {
 public:
   using Op         = b200_detail::ValueLocOp<T, IndexType, true>;
   using value_type = typename Op::value_type;
-  using Base       = b200::detail::Reduce<Op>;
+  using Base       = b200::detail::Reduce<Op, Ordered>;
+  // (T(), IndexType()), as pattern/detail/reduce.hpp:403
+  ReduceMinLoc() : Base(value_type(T(), IndexType()), Op::identity()) {}
   ReduceMinLoc(T init_val, IndexType init_idx, T identity_val = RAJA::operators::limits<T>::max(),
                IndexType identity_idx = RAJA::reduce::detail::DefaultLoc<IndexType>().value())
       : Base(value_type(init_val, init_idx), value_type(identity_val, identity_idx))
@@ -325,13 +316,14 @@ public:
   operator T() { return Base::get(); }
   T get() { return Base::get(); }
 };
-template<typename T, typename IndexType>
-class ReduceMaxLoc<b200_reduce, T, IndexType> : public b200::detail::Reduce<b200_detail::ValueLocOp<T, IndexType, false>>
+template<bool Ordered, typename T, typename IndexType>
+class ReduceMaxLoc<b200_reduce_policy<Ordered>, T, IndexType> : public b200::detail::Reduce<b200_detail::ValueLocOp<T, IndexType, false>, Ordered>
 {
 public:
   using Op         = b200_detail::ValueLocOp<T, IndexType, false>;
   using value_type = typename Op::value_type;
-  using Base       = b200::detail::Reduce<Op>;
+  using Base       = b200::detail::Reduce<Op, Ordered>;
+  ReduceMaxLoc() : Base(value_type(T(), IndexType()), Op::identity()) {}
   ReduceMaxLoc(T init_val, IndexType init_idx, T identity_val = RAJA::operators::limits<T>::min(),
                IndexType identity_idx = RAJA::reduce::detail::DefaultLoc<IndexType>().value())
       : Base(value_type(init_val, init_idx), value_type(identity_val, identity_idx))

@@ -32,9 +32,9 @@ inline resources::EventProxy<resources::Cuda> run(resources::Cuda res, InIter be
 }
 }  // namespace b200_detail
 
-template<size_t BLOCK_SIZE, bool Async, typename InputIter, typename Function>
+template<size_t BLOCK_SIZE, size_t GRID_SIZE, bool Async, typename InputIter, typename Function>
 inline resources::EventProxy<resources::Cuda> inclusive_inplace(resources::Cuda res,
-                                                                 ::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async> const&,
+                                                                 ::RAJA::policy::b200::b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async> const&,
                                                                  InputIter begin,
                                                                  InputIter end,
                                                                  Function binary_op)
@@ -43,9 +43,9 @@ inline resources::EventProxy<resources::Cuda> inclusive_inplace(resources::Cuda 
   return b200_detail::run<true, BLOCK_SIZE, Async>(res, begin, end, begin, binary_op, T {});
 }
 
-template<size_t BLOCK_SIZE, bool Async, typename InputIter, typename Function, typename T>
+template<size_t BLOCK_SIZE, size_t GRID_SIZE, bool Async, typename InputIter, typename Function, typename T>
 inline resources::EventProxy<resources::Cuda> exclusive_inplace(resources::Cuda res,
-                                                                 ::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async> const&,
+                                                                 ::RAJA::policy::b200::b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async> const&,
                                                                  InputIter begin,
                                                                  InputIter end,
                                                                  Function binary_op,
@@ -55,9 +55,9 @@ inline resources::EventProxy<resources::Cuda> exclusive_inplace(resources::Cuda 
   return b200_detail::run<false, BLOCK_SIZE, Async>(res, begin, end, begin, binary_op, (V)init);
 }
 
-template<size_t BLOCK_SIZE, bool Async, typename InputIter, typename OutputIter, typename Function>
+template<size_t BLOCK_SIZE, size_t GRID_SIZE, bool Async, typename InputIter, typename OutputIter, typename Function>
 inline resources::EventProxy<resources::Cuda> inclusive(resources::Cuda res,
-                                                         ::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async> const&,
+                                                         ::RAJA::policy::b200::b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async> const&,
                                                          InputIter begin,
                                                          InputIter end,
                                                          OutputIter out,
@@ -67,9 +67,9 @@ inline resources::EventProxy<resources::Cuda> inclusive(resources::Cuda res,
   return b200_detail::run<true, BLOCK_SIZE, Async>(res, begin, end, out, binary_op, T {});
 }
 
-template<size_t BLOCK_SIZE, bool Async, typename InputIter, typename OutputIter, typename Function, typename T>
+template<size_t BLOCK_SIZE, size_t GRID_SIZE, bool Async, typename InputIter, typename OutputIter, typename Function, typename T>
 inline resources::EventProxy<resources::Cuda> exclusive(resources::Cuda res,
-                                                         ::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async> const&,
+                                                         ::RAJA::policy::b200::b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async> const&,
                                                          InputIter begin,
                                                          InputIter end,
                                                          OutputIter out,

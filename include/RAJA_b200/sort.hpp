@@ -73,23 +73,23 @@ inline resources::EventProxy<resources::Cuda> sort_pairs(resources::Cuda res, Ke
 }
 }  // namespace b200_detail
 
-template<size_t BLOCK_SIZE, bool Async, typename Iter, typename Compare>
-inline resources::EventProxy<resources::Cuda> unstable(resources::Cuda res, ::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async> const&, Iter begin, Iter end, Compare comp)
+template<size_t BLOCK_SIZE, size_t GRID_SIZE, bool Async, typename Iter, typename Compare>
+inline resources::EventProxy<resources::Cuda> unstable(resources::Cuda res, ::RAJA::policy::b200::b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async> const&, Iter begin, Iter end, Compare comp)
 {
   return b200_detail::sort_keys<Async>(res, begin, end, comp);
 }
-template<size_t BLOCK_SIZE, bool Async, typename Iter, typename Compare>
-inline resources::EventProxy<resources::Cuda> stable(resources::Cuda res, ::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async> const&, Iter begin, Iter end, Compare comp)
+template<size_t BLOCK_SIZE, size_t GRID_SIZE, bool Async, typename Iter, typename Compare>
+inline resources::EventProxy<resources::Cuda> stable(resources::Cuda res, ::RAJA::policy::b200::b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async> const&, Iter begin, Iter end, Compare comp)
 {
   return b200_detail::sort_keys<Async>(res, begin, end, comp);
 }
-template<size_t BLOCK_SIZE, bool Async, typename KeyIter, typename ValIter, typename Compare>
-inline resources::EventProxy<resources::Cuda> unstable_pairs(resources::Cuda res, ::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async> const&, KeyIter kb, KeyIter ke, ValIter vb, Compare comp)
+template<size_t BLOCK_SIZE, size_t GRID_SIZE, bool Async, typename KeyIter, typename ValIter, typename Compare>
+inline resources::EventProxy<resources::Cuda> unstable_pairs(resources::Cuda res, ::RAJA::policy::b200::b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async> const&, KeyIter kb, KeyIter ke, ValIter vb, Compare comp)
 {
   return b200_detail::sort_pairs<Async>(res, kb, ke, vb, comp);
 }
-template<size_t BLOCK_SIZE, bool Async, typename KeyIter, typename ValIter, typename Compare>
-inline resources::EventProxy<resources::Cuda> stable_pairs(resources::Cuda res, ::RAJA::policy::b200::b200_exec<BLOCK_SIZE, Async> const&, KeyIter kb, KeyIter ke, ValIter vb, Compare comp)
+template<size_t BLOCK_SIZE, size_t GRID_SIZE, bool Async, typename KeyIter, typename ValIter, typename Compare>
+inline resources::EventProxy<resources::Cuda> stable_pairs(resources::Cuda res, ::RAJA::policy::b200::b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async> const&, KeyIter kb, KeyIter ke, ValIter vb, Compare comp)
 {
   return b200_detail::sort_pairs<Async>(res, kb, ke, vb, comp);
 }

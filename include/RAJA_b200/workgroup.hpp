@@ -325,7 +325,8 @@ struct WorkRunner<RAJA::b200_work<BLOCK_SIZE, Async>, RAJA::unordered_b200_fused
       // pageable source: the driver stages it before returning, so the vector may change afterwards
       RAJA::b200_detail::check(cudaMemcpyAsync(prefix.p, m_tile_end.data(), num_loops * sizeof(unsigned), cudaMemcpyHostToDevice, stream), "workgroup prefix");
       auto kern = &b200_detail::workgroup_fused_kernel<(int)BLOCK_SIZE, Iterator, value_type, Args...>;
-      static thread_local int occ = 0;  // per instantiation and host thread
+      static thread_local ::b200::PerDevice occ_cache;  // per instantiation, host thread and device
+      int& occ = occ_cache.current();
       if (occ == 0)
       {
         RAJA::b200_detail::check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)BLOCK_SIZE, 0), "workgroup occupancy");

@@ -71,6 +71,18 @@ int rb200_sm_count(void);
  * (policy/cuda/synchronize.hpp:39-42) and camp::resources::Cuda::wait(). */
 int rb200_stream_synchronize(rb200_stream_t stream);
 int rb200_device_synchronize(void);
+/* Stream bookkeeping of RAJA::cuda::launch() / RAJA::cuda::synchronize()
+ * (policy/cuda/MemUtils_CUDA.hpp:207-284, g_stream_info_map): every kernel the back-end enqueues marks its
+ * stream as "has work in flight"; rb200_synchronize_streams() waits for exactly the marked streams of the
+ * current device and clears the marks (streams nothing was launched on since the last call are skipped);
+ * rb200_stream_mark_synced() clears one mark after the caller has waited for that stream itself.
+ * Returns the number of streams waited for, or a negative error. */
+void rb200_stream_mark_launch(rb200_stream_t stream);
+void rb200_stream_mark_synced(rb200_stream_t stream);
+int rb200_synchronize_streams(void);
+/* NVTX range around a named launch: RAJA::Name (policy/cuda/params/kernel_name.hpp:28-71) */
+void rb200_range_push(const char* name);
+void rb200_range_pop(void);
 
 /* ---- launch accounting / profiling (no reference counterpart; bench.py uses it) -------
  * Every kernel the library launches is counted.  With profiling enabled each launch is

@@ -24,6 +24,11 @@ SIGNATURES = {
     "rb200_sm_count": (c_int, []),
     "rb200_stream_synchronize": (c_int, [c_void_p]),
     "rb200_device_synchronize": (c_int, []),
+    "rb200_stream_mark_launch": (None, [c_void_p]),
+    "rb200_stream_mark_synced": (None, [c_void_p]),
+    "rb200_synchronize_streams": (c_int, []),
+    "rb200_range_push": (None, [ctypes.c_char_p]),
+    "rb200_range_pop": (None, []),
     "rb200_launch_count": (ctypes.c_longlong, []),
     "rb200_profile_enable": (c_int, [c_int]),
     "rb200_profile_reset": (c_int, []),

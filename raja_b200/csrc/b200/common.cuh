@@ -44,6 +44,19 @@ inline const DeviceInfo& device_info()
   return info[dev];
 }
 
+// A per-call-site cache with one slot per device ordinal: function attributes (the > 48 KB shared-memory
+// opt-in) and occupancy are properties of (kernel, device), so a host thread that moves between devices
+// with cudaSetDevice must not reuse what it learned on another one.
+struct PerDevice {
+  int v[64] = {};
+  int& current()
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return v[(dev >= 0 && dev < 64) ? dev : 0];
+  }
+};
+
 // ---------------------------------------------------------------------------
 // Launch hook: every kernel launch of the back-end is bracketed by these calls so
 // a host (libraja_b200's profiler, rb200_profile_*) can count launches and time
@@ -115,6 +128,15 @@ template <class T> struct BitAnd {
   B200_HD static T identity() { return ~T(0); }
   B200_HD T operator()(T a, T b) const { return a & b; }
 };
+
+// Operators known to be commutative may be folded in any fixed order; anything else (user functors wrapped by the
+// policy layer) is only assumed associative and is folded strictly left to right.
+template <class Op> struct is_commutative : std::false_type {};
+template <class T> struct is_commutative<Plus<T>> : std::true_type {};
+template <class T> struct is_commutative<Minimum<T>> : std::true_type {};
+template <class T> struct is_commutative<Maximum<T>> : std::true_type {};
+template <class T> struct is_commutative<BitOr<T>> : std::true_type {};
+template <class T> struct is_commutative<BitAnd<T>> : std::true_type {};
 
 // (value, location) pair for Min/MaxLoc.  The reference's sequential fold keeps
 // the FIRST (lowest-iteration) extremum (pattern/detail/reduce.hpp:127-179 and

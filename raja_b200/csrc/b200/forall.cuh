@@ -98,8 +98,9 @@ inline int persistent_grid(int occ_per_sm, long long tiles)
 template <int BLOCK, int UNROLL, class Index, class Body, class Finalize>
 inline int forall_occupancy()
 {
-  // occupancy is a property of the instantiation; query once per host thread
-  static thread_local int cached = 0;
+  // occupancy is a property of the instantiation and the device; query once per host thread and device
+  static thread_local PerDevice cache;
+  int& cached = cache.current();
   if (cached == 0) {
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, forall_kernel<BLOCK, UNROLL, Index, Body, Finalize>, BLOCK, 0);
@@ -109,11 +110,12 @@ inline int forall_occupancy()
 }
 
 template <int BLOCK, int UNROLL, class Index, class Body, class Finalize>
-inline int forall_grid(Index len)
+inline int forall_grid(Index len, long long fixed_grid = 0)
 {
   // full tiles + the BLOCK-sized chunks of the ragged last tile (each chunk may go to a block of its own)
   const long long tile = (long long)BLOCK * UNROLL, full = (long long)len / tile;
   const long long units = full + ((long long)len - full * tile + BLOCK - 1) / BLOCK;
+  if (fixed_grid > 0) return (int)(fixed_grid < units ? fixed_grid : (units < 1 ? 1 : units));  // a grid the caller fixed
   return persistent_grid(forall_occupancy<BLOCK, UNROLL, Index, Body, Finalize>(), units);
 }
 

@@ -1107,14 +1107,15 @@ template <class U, class VT, class S = typename Tuning<U, VT>::shape> inline siz
 }
 
 // opt-in to > 48 KB of dynamic shared memory, once per kernel (keyed on the kernel itself:
-// kernels of one signature share a function-pointer TYPE) and host thread
+// kernels of one signature share a function-pointer TYPE), host thread and device
 template <auto Kern> inline cudaError_t configure_once(int smem_bytes)
 {
-  static thread_local bool configured = false;
+  static thread_local PerDevice cache;
+  int& configured = cache.current();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured = 1;
   }
   return cudaSuccess;
 }

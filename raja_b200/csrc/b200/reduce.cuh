@@ -92,6 +92,19 @@ template <class Op> B200_D typename Op::value_type warp_allreduce(typename Op::v
   }
 }
 
+// strictly left-to-right (lane 0 leftmost) for operators that are associative but not commutative:
+// adjacent lanes first, so every partial is a fold of a contiguous run of lanes
+template <class Op> B200_D typename Op::value_type warp_allreduce_ordered(typename Op::value_type v, Op op)
+{
+  using T = typename Op::value_type;
+#pragma unroll
+  for (int m = 1; m <= 16; m <<= 1) {
+    T o = shfl_xor(v, m);
+    v = (lane_id() & m) ? op(o, v) : op(v, o);
+  }
+  return v;
+}
+
 // ---- block reduce: result valid in every thread of warp 0 ---------------------
 // smem must hold 32 values of T and may be reused after the call returns only
 // after a __syncthreads().
@@ -169,6 +182,78 @@ B200_D bool grid_combine_last_block(typename Op::value_type block_val,
   result = block_reduce<BLOCK>(acc, op, smem);
   return true;
 }
+
+// ---- self-resetting atomic slot (the unordered grid combine) --------------------
+// One 8-byte device word that is ZERO when idle: blocks combine into it with one hardware atomic each, the block
+// that arrives last takes the result out with an exchange that leaves zero behind, so the word goes back to a
+// zeroed pool without a memset and needs no per-launch initialisation with the operator's identity.
+//   plus        the value itself (the identity's bit pattern is zero)
+//   max / min   atomicMax on an order-preserving unsigned code of v (min: of its complement); 0 = "nothing yet"
+//   or / and    atomicOr on v (and: on ~v, De Morgan)
+// available == false for operators / value types the ISA has no atomic for (callers fall back to the ordered combine,
+// as the reference's atomic tunings do: policy/cuda/reduce.hpp:1001-1030).
+template <class T> struct order_code {
+  using U = typename std::conditional<sizeof(T) == 4, unsigned, unsigned long long>::type;
+  static constexpr U SIGN = U(1) << (8 * sizeof(T) - 1);
+  B200_D static U enc(T v)
+  {
+    U b = bit_cast_<U>(v);
+    if constexpr (std::is_floating_point<T>::value) return (b & SIGN) ? ~b : (b | SIGN);
+    else if constexpr (std::is_signed<T>::value) return b ^ SIGN;
+    else return b;
+  }
+  B200_D static T dec(U c)
+  {
+    if constexpr (std::is_floating_point<T>::value) return bit_cast_<T>((c & SIGN) ? (c ^ SIGN) : ~c);
+    else if constexpr (std::is_signed<T>::value) return bit_cast_<T>(U(c ^ SIGN));
+    else return bit_cast_<T>(c);
+  }
+};
+template <class Op, class = void> struct AtomicSlot {
+  static constexpr bool available = false;
+};
+template <class T> struct AtomicSlot<Plus<T>, std::enable_if_t<std::is_arithmetic<T>::value && (sizeof(T) == 4 || sizeof(T) == 8)>> {
+  static constexpr bool available = true;
+  using U = typename order_code<T>::U;
+  B200_D static void combine(void* slot, T v)
+  {
+    if constexpr (std::is_floating_point<T>::value) atomicAdd(reinterpret_cast<T*>(slot), v);
+    else atomicAdd(reinterpret_cast<U*>(slot), bit_cast_<U>(v));  // two's complement: one add for signed and unsigned
+  }
+  B200_D static T take(void* slot) { return bit_cast_<T>(atomicExch(reinterpret_cast<U*>(slot), U(0))); }
+};
+template <class T> struct AtomicSlot<Maximum<T>, std::enable_if_t<std::is_arithmetic<T>::value && (sizeof(T) == 4 || sizeof(T) == 8)>> {
+  static constexpr bool available = true;
+  using U = typename order_code<T>::U;
+  B200_D static void combine(void* slot, T v) { atomicMax(reinterpret_cast<U*>(slot), order_code<T>::enc(v)); }
+  B200_D static T take(void* slot)
+  {
+    const U c = atomicExch(reinterpret_cast<U*>(slot), U(0));
+    return c == 0 ? Maximum<T>::identity() : order_code<T>::dec(c);
+  }
+};
+template <class T> struct AtomicSlot<Minimum<T>, std::enable_if_t<std::is_arithmetic<T>::value && (sizeof(T) == 4 || sizeof(T) == 8)>> {
+  static constexpr bool available = true;
+  using U = typename order_code<T>::U;
+  B200_D static void combine(void* slot, T v) { atomicMax(reinterpret_cast<U*>(slot), U(~order_code<T>::enc(v))); }
+  B200_D static T take(void* slot)
+  {
+    const U c = atomicExch(reinterpret_cast<U*>(slot), U(0));
+    return c == 0 ? Minimum<T>::identity() : order_code<T>::dec(U(~c));
+  }
+};
+template <class T> struct AtomicSlot<BitOr<T>, std::enable_if_t<std::is_integral<T>::value && (sizeof(T) == 4 || sizeof(T) == 8)>> {
+  static constexpr bool available = true;
+  using U = typename order_code<T>::U;
+  B200_D static void combine(void* slot, T v) { atomicOr(reinterpret_cast<U*>(slot), bit_cast_<U>(v)); }
+  B200_D static T take(void* slot) { return bit_cast_<T>(atomicExch(reinterpret_cast<U*>(slot), U(0))); }
+};
+template <class T> struct AtomicSlot<BitAnd<T>, std::enable_if_t<std::is_integral<T>::value && (sizeof(T) == 4 || sizeof(T) == 8)>> {
+  static constexpr bool available = true;
+  using U = typename order_code<T>::U;
+  B200_D static void combine(void* slot, T v) { atomicOr(reinterpret_cast<U*>(slot), U(~bit_cast_<U>(v))); }
+  B200_D static T take(void* slot) { return bit_cast_<T>(U(~atomicExch(reinterpret_cast<U*>(slot), U(0)))); }
+};
 
 // Unordered variant ("b200_reduce_atomic"): one atomic per block on the target.
 // Only defined for the types/ops the ISA has atomics for.

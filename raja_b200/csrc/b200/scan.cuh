@@ -6,9 +6,10 @@
 //
 //   * persistent grid (SMs x resident CTAs); a CTA takes a virtual id from an
 //     atomic ticket and then owns tiles vid, vid+G, vid+2G, ...  A CTA that holds
-//     virtual id v was started after every id < v, and each CTA works through its
-//     tiles in ascending order, so the lowest unfinished tile is always being
-//     worked on: look-back cannot deadlock whatever the block scheduler does;
+//     virtual id v was started after every id < v.  A tile of a CTA's SECOND round looks
+//     back at tiles of higher virtual ids, so multi-round grids need every CTA resident:
+//     they are launched cooperatively (gang-scheduled, fails instead of hanging when the
+//     grid cannot fit) and the look-back spin is bounded (trap after ~10 s);
 //   * each tile is brought into shared memory by ONE bulk async copy
 //     (cp.async.bulk global->shared, completion on an mbarrier) issued three tiles
 //     ahead, and leaves through ONE bulk async copy shared->global: without the
@@ -149,6 +150,8 @@ scan_kernel(const T* in, T* out, const long long n, const T init, const T* carry
   constexpr int V = L::V, ITEMS = L::ITEMS, TILE = L::TILE, NW = L::NW;
   using VT = Vec<T, V>;
 
+  constexpr bool COMMUTATIVE = is_commutative<Op>::value;
+  constexpr unsigned SPIN_LIMIT = 1u << 26;  // ~10 s of 64 ns naps plus the poll itself
   extern __shared__ __align__(128) unsigned char smem[];
   T* const tiles = reinterpret_cast<T*>(smem);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
@@ -257,7 +260,9 @@ scan_kernel(const T* in, T* out, const long long n, const T init, const T* carry
     lb_ok = true;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-      const long long d = (long long)r * WARP + l + 1;
+      // commutative operators: lane-interleaved distances (coalesced polls); otherwise every lane owns a CONTIGUOUS
+      // run of predecessors so that the fold below is strictly left to right
+      const long long d = COMMUTATIVE ? (long long)r * WARP + l + 1 : (long long)l * ROWS + r + 1;
       lb_val[r] = ident;
       if (d <= dist) lb_ok = ts.peek(tile - d, lb_val[r]) && lb_ok;
     }
@@ -269,14 +274,17 @@ scan_kernel(const T* in, T* out, const long long n, const T init, const T* carry
     while (!__all_sync(FULL_MASK, lb_ok)) {
       __nanosleep(64);
       poll(i);
-      ++polls;
+      // a predecessor that never publishes (its CTA never became resident) must end in an error, not a hang
+      if (++polls > SPIN_LIMIT) __trap();
     }
     // fixed fold order: per lane farthest row first, then lanes farthest (highest) first
     T c = ident;
 #pragma unroll
     for (int r = ROWS - 1; r >= 0; --r) c = op(c, lb_val[r]);
     T rc = shfl_idx(c, WARP - 1 - l);
-    T window = warp_allreduce(rc, op);
+    T window;
+    if constexpr (COMMUTATIVE) window = warp_allreduce(rc, op);
+    else window = warp_allreduce_ordered(rc, op);
     if (trace && l == 0) trace[tile] = polls;
     return op((tile >= 2 * G) ? base_2back : seed, window);
   };
@@ -448,7 +456,8 @@ template <class T, class Op, bool Inclusive, class S>
 inline cudaError_t configure(int* ctas_per_sm)
 {
   auto kern = scan_kernel<T, Op, Inclusive, S>;
-  static thread_local int cached = 0;
+  static thread_local PerDevice cache;  // the opt-in and the occupancy are per (kernel, device)
+  int& cached = cache.current();
   if (cached == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Layout<T, S>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
@@ -484,6 +493,16 @@ inline cudaError_t launch(cudaStream_t stream, const T* in, T* out, long long n,
   if (((uintptr_t)out & 15u) == 0) flags |= F_BULK_OUT;
   flags = (flags & ~flags_clear) | flags_set;
   LaunchScope scope("scan_kernel", stream);
+  if (ntiles > grid) {
+    // A CTA that owns several tiles (vid, vid + G, ...) looks back at tiles of CTAs with HIGHER ticket numbers, so
+    // every CTA of the grid must be resident: a cooperative launch is gang-scheduled (it starts only when the whole
+    // grid fits, e.g. after another scan on another stream has drained) and fails instead of hanging when it cannot.
+    unsigned* ticket = (unsigned*)workspace;
+    void* args[] = {(void*)&in, (void*)&out, (void*)&n, (void*)&init, (void*)&carry_dev, (void*)&ts, (void*)&ticket, (void*)&flags, (void*)&trace};
+    return cudaLaunchCooperativeKernel((const void*)scan_kernel<T, Op, Inclusive, S>, dim3((unsigned)grid), dim3(S::THREADS), args,
+                                       Layout<T, S>::SMEM_BYTES, stream);
+  }
+  // one tile per CTA: a tile only looks back at lower tickets, i.e. at CTAs that have already started
   scan_kernel<T, Op, Inclusive, S><<<(unsigned)grid, S::THREADS, Layout<T, S>::SMEM_BYTES, stream>>>(in, out, n, init, carry_dev, ts,
                                                                                                       (unsigned*)workspace, flags, trace);
   return cudaGetLastError();

@@ -144,6 +144,7 @@ int pool_free(PoolKind kind, void* p, cudaStream_t stream)
 #include "b200/common.cuh"
 #include <atomic>
 #include <cstring>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: resolves the tool's injection library at run time (no-ops without one)
 
 namespace rb200 {
 namespace {
@@ -157,9 +158,25 @@ std::mutex g_prof_mu;
 std::vector<LaunchRecord> g_records;
 thread_local cudaEvent_t tl_e1 = nullptr;
 
+// streams with launches in flight since they were last waited for, per device
+// (the role of g_stream_info_map, policy/cuda/MemUtils_CUDA.hpp:207-247)
+std::mutex g_streams_mu;
+std::vector<std::pair<int, cudaStream_t>> g_dirty_streams;
+
+void mark_launch(cudaStream_t stream)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(g_streams_mu);
+  for (auto& e : g_dirty_streams)
+    if (e.first == dev && e.second == stream) return;
+  g_dirty_streams.emplace_back(dev, stream);
+}
+
 void hook_begin(const char* name, cudaStream_t stream)
 {
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  mark_launch(stream);
   tl_e1 = nullptr;
   if (!g_profile.load(std::memory_order_relaxed)) return;
   cudaEvent_t e0, e1;
@@ -244,6 +261,50 @@ int rb200_device_synchronize(void)
   RB200_CUDA(cudaDeviceSynchronize());
   return 0;
 }
+
+void rb200_stream_mark_launch(rb200_stream_t stream) { mark_launch((cudaStream_t)stream); }
+void rb200_stream_mark_synced(rb200_stream_t stream)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(g_streams_mu);
+  for (size_t i = 0; i < g_dirty_streams.size(); ++i)
+    if (g_dirty_streams[i].first == dev && g_dirty_streams[i].second == (cudaStream_t)stream) {
+      g_dirty_streams.erase(g_dirty_streams.begin() + i);
+      return;
+    }
+}
+int rb200_synchronize_streams(void)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::vector<cudaStream_t> todo;
+  {
+    std::lock_guard<std::mutex> g(g_streams_mu);
+    for (size_t i = 0; i < g_dirty_streams.size();) {
+      if (g_dirty_streams[i].first == dev) {
+        todo.push_back(g_dirty_streams[i].second);
+        g_dirty_streams.erase(g_dirty_streams.begin() + i);
+      } else {
+        ++i;
+      }
+    }
+  }
+  for (cudaStream_t s : todo) {
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+      cuda_fail(e, "rb200_synchronize_streams");
+      return RB200_EINVAL;
+    }
+  }
+  return (int)todo.size();
+}
+
+void rb200_range_push(const char* name)
+{
+  if (name) nvtxRangePushA(name);
+}
+void rb200_range_pop(void) { nvtxRangePop(); }
 
 void* rb200_device_malloc(size_t bytes, rb200_stream_t s) { return pool_malloc(POOL_DEVICE, bytes, (cudaStream_t)s); }
 void* rb200_device_zeroed_malloc(size_t bytes, rb200_stream_t s) { return pool_malloc(POOL_DEVICE_ZEROED, bytes, (cudaStream_t)s); }
