@@ -9,6 +9,7 @@
 //     RAJA::b200_atomic, b200_atomic_aggregated (atomicAdd & friends)
 //     RAJA::b200_synchronize
 //     RAJA::b200_launch_t<Async>            (RAJA::launch, with or without expt::Reduce params)
+//     RAJA::statement::B200Kernel<...>      (RAJA::kernel / kernel_param, with or without expt::Reduce params)
 //     RAJA::b200_work<BLOCK, Async>, RAJA::unordered_b200_fused   (WorkPool / WorkGroup / WorkSite)
 //     RAJA::b200::{device,device_zeroed,pinned}_mempool_type
 //
@@ -80,6 +81,7 @@
 #include "RAJA_b200/reduce.hpp"
 #include "RAJA_b200/multi_reduce.hpp"
 #include "RAJA_b200/launch.hpp"
+#include "RAJA_b200/kernel.hpp"
 #include "RAJA_b200/workgroup.hpp"
 
 #endif  // RAJA_B200_RAJA_HPP

@@ -159,6 +159,22 @@ struct LaunchScope
   ~LaunchScope() { tl_launch().active = false; }
 };
 
+// The header-only engine brackets every launch with b200::launch_hook() (b200/common.cuh).  Kernels instantiated in the
+// user's translation unit report to the library through its exported entry points, so they are counted, marked on their
+// stream (RAJA::synchronize<b200_synchronize>) and profiled like the library's own -- whatever the symbol binding between
+// the executable and the shared library is.
+inline void hook_begin(const char* name, cudaStream_t s) { rb200_launch_begin(name, s); }
+inline void hook_end(const char* name, cudaStream_t s) { rb200_launch_end(name, s); }
+struct HookInstaller
+{
+  HookInstaller()
+  {
+    ::b200::launch_hook().begin = hook_begin;
+    ::b200::launch_hook().end   = hook_end;
+  }
+};
+static const HookInstaller hook_installer_instance;  // one per translation unit; idempotent
+
 // scratch from the stream-ordered pool, returned on scope exit (safe right after enqueue)
 struct Scratch
 {

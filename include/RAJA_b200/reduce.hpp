@@ -15,7 +15,8 @@ namespace b200_detail
 {
 // ---- min/max over (value, location) pairs: ties go to the smaller location, which makes the parallel
 //      tree return what the sequential loop returns -- the FIRST extremum (util/Operators.hpp:555-594:
-//      ties keep the left operand).  A location of -1 marks "no element yet" (expt::ValLoc's default).
+//      ties keep the left operand).  A location of -1 marks "no element yet" (expt::ValLoc's default) and counts as the
+//      smallest: a sequential accumulator that starts at the identity keeps it when an element ties with it.
 template<class T, class I>
 struct kernel_op<RAJA::operators::minimum<RAJA::expt::ValLoc<T, I>, RAJA::expt::ValLoc<T, I>, RAJA::expt::ValLoc<T, I>>, RAJA::expt::ValLoc<T, I>, void>
 {
@@ -25,8 +26,9 @@ struct kernel_op<RAJA::operators::minimum<RAJA::expt::ValLoc<T, I>, RAJA::expt::
     RAJA_HOST_DEVICE static value_type identity() { return RAJA::operators::minimum<value_type, value_type, value_type>::identity(); }
     RAJA_HOST_DEVICE value_type operator()(value_type a, value_type b) const
     {
-      const bool take_b = (b.val < a.val) || (!(a.val < b.val) && b.loc != I(-1) && (a.loc == I(-1) || b.loc < a.loc));
-      return take_b ? b : a;
+      bool take_b = (b.val < a.val);
+      if constexpr (std::is_integral<I>::value) take_b = take_b || (!(a.val < b.val) && a.loc != I(-1) && (b.loc == I(-1) || b.loc < a.loc));
+      return take_b ? b : a;  // location types without an order (user structs): a tie keeps the left operand
     }
   };
 };
@@ -39,7 +41,8 @@ struct kernel_op<RAJA::operators::maximum<RAJA::expt::ValLoc<T, I>, RAJA::expt::
     RAJA_HOST_DEVICE static value_type identity() { return RAJA::operators::maximum<value_type, value_type, value_type>::identity(); }
     RAJA_HOST_DEVICE value_type operator()(value_type a, value_type b) const
     {
-      const bool take_b = (a.val < b.val) || (!(b.val < a.val) && b.loc != I(-1) && (a.loc == I(-1) || b.loc < a.loc));
+      bool take_b = (a.val < b.val);
+      if constexpr (std::is_integral<I>::value) take_b = take_b || (!(b.val < a.val) && a.loc != I(-1) && (b.loc == I(-1) || b.loc < a.loc));
       return take_b ? b : a;
     }
   };

@@ -30,6 +30,22 @@
 
 namespace RAJA
 {
+namespace b200_detail
+{
+// host-side fold of (initial value, launch 1, launch 2, ...): operators that distinguish "in order" from "in a tree"
+// (the value-location pairs below) provide Op::fold_in_order; everything else folds with the operator itself
+template<class Op, class V>
+inline auto fold_in_order(Op, V a, V b, int) -> decltype(Op::fold_in_order(a, b))
+{
+  return Op::fold_in_order(a, b);
+}
+template<class Op, class V>
+inline V fold_in_order(Op op, V a, V b, long)
+{
+  return op(a, b);
+}
+}  // namespace b200_detail
+
 namespace b200
 {
 namespace detail
@@ -144,7 +160,7 @@ public:
       for (cudaStream_t s : c->streams) ::RAJA::b200_detail::check(cudaStreamSynchronize(s), "reducer get");
       c->streams.clear();
       Op op;
-      for (size_t i = 0; i < c->used; ++i) m_value = op(m_value, *c->slot(i));
+      for (size_t i = 0; i < c->used; ++i) m_value = ::RAJA::b200_detail::fold_in_order(op, m_value, *c->slot(i), 0);
       c->used = 0;
     }
     return m_value;
@@ -220,12 +236,22 @@ struct ValueLocOp
     bool take_b       = better;
     if constexpr (std::is_integral<I>::value)
     {
+      // ties inside the parallel tree: the smaller location wins and "no location" (the identity's, DefaultLoc) counts as
+      // the smallest -- in the sequential fold an accumulator that starts at the identity keeps it on a tie
       const I none = RAJA::reduce::detail::DefaultLoc<I>().value();
-      if (!better && !worse) take_b = (b.getLoc() != none) && (a.getLoc() == none || b.getLoc() < a.getLoc());
+      if (!better && !worse) take_b = (a.getLoc() != none) && (b.getLoc() == none || b.getLoc() < a.getLoc());
     }
     return take_b ? b : a;
   }
+  // host-side fold of (initial value, launch 1, launch 2, ...): the order is known, so a tie keeps the left operand exactly
+  // as the sequential loop does (util/Operators.hpp:555-594) -- e.g. an initial value that equals the minimum keeps its location
+  RAJA_HOST_DEVICE static value_type fold_in_order(value_type a, value_type b)
+  {
+    const T av = a, bv = b;
+    return (doing_min ? (bv < av) : (av < bv)) ? b : a;
+  }
 };
+
 }  // namespace b200_detail
 
 // ---- the specialisations user code names (primary templates: pattern/reduce.hpp:80-233) -----------------

@@ -80,6 +80,11 @@ int rb200_device_synchronize(void);
 void rb200_stream_mark_launch(rb200_stream_t stream);
 void rb200_stream_mark_synced(rb200_stream_t stream);
 int rb200_synchronize_streams(void);
+/* Launch accounting for kernels instantiated OUTSIDE the library from the same header-only engine (the RAJA policy layer
+ * in the user's translation unit): bracket each launch with these two calls and it is counted, marked on its stream and --
+ * with profiling enabled -- timed like the library's own launches. */
+void rb200_launch_begin(const char* kernel, rb200_stream_t stream);
+void rb200_launch_end(const char* kernel, rb200_stream_t stream);
 /* NVTX range around a named launch: RAJA::Name (policy/cuda/params/kernel_name.hpp:28-71) */
 void rb200_range_push(const char* name);
 void rb200_range_pop(void);
@@ -194,6 +199,21 @@ int rb200_comm_barrier(rb200_comm_t c, rb200_stream_t stream);
 int rb200_comm_exchange_pairs(rb200_comm_t c, rb200_dtype key_t, const void* keys_in, const void* vals_in, int val_bytes,
                               int64_t n, const void* splitters_host, int nsplit, int descending, size_t recv_keys_offset,
                               size_t recv_vals_offset, int64_t recv_capacity, int64_t* n_received, rb200_stream_t stream);
+/* The whole exchange step of the sample sort without host-side plumbing: a regular sample of the UNSORTED shard
+ * (samples_per_rank keys, <= 4096) is all-gathered through peer memory, every rank sorts the same gathered samples on its
+ * device and picks the world - 1 splitters there (no splitter ever visits the host), then the fused partition + all-to-all
+ * of rb200_comm_exchange_pairs runs with them.  One host synchronisation remains (the count matrix: the caller needs
+ * *n_received).  RB200_ENOMEM -- returned by EVERY rank, they all see the same count matrix -- when some rank would receive
+ * more than recv_capacity elements (heavily duplicated keys): the caller falls back to a collective all-to-all. */
+int rb200_comm_sample_exchange_pairs(rb200_comm_t c, rb200_dtype key_t, const void* keys_in, const void* vals_in, int val_bytes, int64_t n,
+                                     int samples_per_rank, int descending, size_t recv_keys_offset, size_t recv_vals_offset,
+                                     int64_t recv_capacity, int64_t* n_received, rb200_stream_t stream);
+/* count elements of dtype t (count * size <= 504 bytes; src_dev 8-byte aligned) combined over the ranks IN RANK ORDER (run-to-run
+ * deterministic for floating point): exclusive_prefix == 0: every rank receives the fold over all ranks (all-reduce);
+ * exclusive_prefix != 0: rank r receives the fold over the ranks below it, the identity on rank 0 (the carry of a sharded scan).
+ * One 1-CTA kernel over peer memory, stream ordered, no host synchronisation. */
+int rb200_comm_allreduce_small(rb200_comm_t c, rb200_op op, rb200_dtype t, const void* src_dev, void* dst_dev, int count, int exclusive_prefix,
+                               rb200_stream_t stream);
 
 /* ---- atomics: policy/cuda/atomic.hpp:665-860 (atomicAdd) ----------------------------------- */
 /* hist[keys[i]] += 1 for i in [0,n)  (exercises/atomic-histogram_solution.cpp:199-202).

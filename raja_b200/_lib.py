@@ -27,6 +27,8 @@ SIGNATURES = {
     "rb200_stream_mark_launch": (None, [c_void_p]),
     "rb200_stream_mark_synced": (None, [c_void_p]),
     "rb200_synchronize_streams": (c_int, []),
+    "rb200_launch_begin": (None, [ctypes.c_char_p, c_void_p]),
+    "rb200_launch_end": (None, [ctypes.c_char_p, c_void_p]),
     "rb200_range_push": (None, [ctypes.c_char_p]),
     "rb200_range_pop": (None, []),
     "rb200_launch_count": (ctypes.c_longlong, []),
@@ -61,6 +63,9 @@ SIGNATURES = {
     "rb200_comm_barrier": (c_int, [c_void_p, c_void_p]),
     "rb200_comm_exchange_pairs": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_size_t, c_size_t, c_int64,
                                           ctypes.POINTER(c_int64), c_void_p]),
+    "rb200_comm_sample_exchange_pairs": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_size_t, c_size_t, c_int64,
+                                                 ctypes.POINTER(c_int64), c_void_p]),
+    "rb200_comm_allreduce_small": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "rb200_atomic_histogram": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "rb200_atomic_pi": (c_int, [c_void_p, c_int64, c_int, c_void_p]),
 }

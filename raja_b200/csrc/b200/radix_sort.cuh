@@ -598,6 +598,7 @@ template <class U> struct SplitDigit {
   U s[MAX_SPLITTERS];  // already mapped with to_ordered(), non-decreasing
   int nsplit;
   KeyOrder order;
+  B200_D U splitter(int i) const { return s[i]; }
   B200_D unsigned operator()(U k) const
   {
     const U ok = to_ordered(k, order);
@@ -613,7 +614,7 @@ template <class U> struct SplitDigit {
 // (peer-mapped memory of GPU d over NVLink), at the positions the pass's bin bases give inside
 // that buffer.  This is the fused "partition + all-to-all" of the multi-GPU sample sort: the
 // write-out of the sweep IS the exchange.
-template <class U, class VT> struct PeerSplitDigit : SplitDigit<U> {
+template <class U, class VT, class Base = SplitDigit<U>> struct PeerSplitDigit : Base {
   static constexpr bool PEER_OUT = true;
   U* kdst[MAX_SPLITTERS + 1];
   VT* vdst[MAX_SPLITTERS + 1];
@@ -1223,7 +1224,7 @@ B200_D void bucket_count_body(const U* __restrict__ keys, const long long n, uns
     const U ok = to_ordered(k, digit.order);
     ++seen;
 #pragma unroll
-    for (int i = 0; i < NS; ++i) c[i] += (ok >= digit.s[i]) ? 1u : 0u;
+    for (int i = 0; i < NS; ++i) c[i] += (ok >= digit.splitter(i)) ? 1u : 0u;
   };
   constexpr int VEC = 16 / sizeof(U), UNROLL = 4;
   using V = Vec<U, VEC>;
@@ -1292,8 +1293,8 @@ template <class U, class VT, class S = typename PartitionTuning<U, VT>::shape> i
 }
 
 // bucket sizes of a split: counts_dev[0 .. MAX_SPLITTERS] (u64, device); workspace as for partition()
-template <class U, class VT, class S = typename PartitionTuning<U, VT>::shape>
-inline cudaError_t bucket_counts(cudaStream_t stream, const U* keys_in, long long n, const SplitDigit<U>& digit, unsigned long long* counts_dev, void* workspace)
+template <class U, class VT, class S = typename PartitionTuning<U, VT>::shape, class DigitFn = SplitDigit<U>>
+inline cudaError_t bucket_counts(cudaStream_t stream, const U* keys_in, long long n, const DigitFn& digit, unsigned long long* counts_dev, void* workspace)
 {
   constexpr int NPASS = sizeof(U);
   const size_t header = (size_t)NPASS * RADIX * 8 * 2 + 256;
@@ -1309,7 +1310,7 @@ inline cudaError_t bucket_counts(cudaStream_t stream, const U* keys_in, long lon
     const long long cap = (long long)device_info().sm_count * 4;
     if (grid > cap) grid = cap;
     LaunchScope scope("bucket_count_kernel", stream);
-    bucket_count_kernel<U, SplitDigit<U>, CB><<<(unsigned)grid, CB, 0, stream>>>(keys_in, n, ghist, digit);
+    bucket_count_kernel<U, DigitFn, CB><<<(unsigned)grid, CB, 0, stream>>>(keys_in, n, ghist, digit);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }

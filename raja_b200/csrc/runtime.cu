@@ -300,6 +300,9 @@ int rb200_synchronize_streams(void)
   return (int)todo.size();
 }
 
+void rb200_launch_begin(const char* kernel, rb200_stream_t stream) { hook_begin(kernel, (cudaStream_t)stream); }
+void rb200_launch_end(const char* kernel, rb200_stream_t stream) { hook_end(kernel, (cudaStream_t)stream); }
+
 void rb200_range_push(const char* name)
 {
   if (name) nvtxRangePushA(name);

@@ -97,6 +97,19 @@ class PeerComm:
         check(lib.rb200_comm_allgather_small(self.handle, src.data_ptr(), nb + pad, out.data_ptr(), res.handle), "comm_allgather_small")
         return out[:, :nb].contiguous().view(t.dtype).reshape(self.world, *t.shape)
 
+    def allreduce_small(self, t, op, res, exclusive_prefix=False):
+        """t: small contiguous device tensor (<= 504 bytes) -> same shape: the fold with rb200_op `op` over all ranks, in rank
+        order (exclusive_prefix: over the ranks below this one; the identity on rank 0).  One peer-memory kernel, no host sync."""
+        from ._lib import lib, check
+        from . import api
+        src = t.contiguous()
+        if src.data_ptr() % 8:
+            src = src.clone()
+        out = torch.empty_like(src)
+        check(lib.rb200_comm_allreduce_small(self.handle, int(op), api._dt(src), src.data_ptr(), out.data_ptr(), src.numel(), int(bool(exclusive_prefix)),
+                                             res.handle), "comm_allreduce_small")
+        return out
+
     def barrier(self, res):
         from ._lib import lib, check
         check(lib.rb200_comm_barrier(self.handle, res.handle), "comm_barrier")
@@ -126,6 +139,30 @@ class PeerComm:
         kout = self.buf[koff:koff + n_out * ks].view(keys.dtype)
         vout = self.buf[voff:voff + n_out * vb].view(vals.dtype) if vb else None
         return kout, vout
+
+
+def _peer_sample_exchange(comm, keys, vals, samples, descending, res):
+    """sampling, splitter selection (on the device), fused partition + all-to-all -> (keys_recv, vals_recv) views of this
+    rank's receive buffers, or None when some rank's share does not fit (decided identically on every rank)"""
+    import ctypes
+    from ._lib import lib, check, B200Error
+    from . import api
+    ks, vb = keys.element_size(), (vals.element_size() if vals is not None else 0)
+    cap = comm.capacity(ks, vb)
+    if cap <= 0:
+        return None
+    koff = comm.header
+    voff = koff + ((cap * ks + 127) // 128) * 128
+    got = ctypes.c_int64(0)
+    rc = lib.rb200_comm_sample_exchange_pairs(comm.handle, api._dt(keys), keys.data_ptr(), vals.data_ptr() if vb else None, vb, keys.numel(),
+                                              int(samples), int(descending), koff, voff, cap, ctypes.byref(got), res.handle)
+    if rc == -3:  # RB200_ENOMEM on every rank: fall back to the collective path
+        return None
+    check(rc, "comm_sample_exchange_pairs")
+    n_out = int(got.value)
+    kout = comm.buf[koff:koff + n_out * ks].view(keys.dtype)
+    vout = comm.buf[voff:voff + n_out * vb].view(vals.dtype) if vb else None
+    return kout, vout
 
 
 class B200Ops:
@@ -227,10 +264,9 @@ def forall_daxpy(rng, a, b, s, ops=None):
 def _allreduce(rng, val, red, res=None):
     if rng.world > 1:
         if rng.comm is not None and res is not None:
-            # one peer-memory all-gather, folded in rank order (deterministic for floating point)
-            g = rng.comm.allgather_small(val, res)
+            # one peer-memory kernel: all-gather + fold in rank order (deterministic for floating point)
             op = {dist.ReduceOp.SUM: 0, dist.ReduceOp.MIN: 1, dist.ReduceOp.MAX: 2}[red]
-            val.copy_(_fold(op, g))
+            val = rng.comm.allreduce_small(val, op, res)
         else:
             dist.all_reduce(val, op=red, group=rng.group)
     return val
@@ -300,15 +336,15 @@ def _scan(rng, inclusive, src, dst, op, init, ops, res):
         # shard total -> all_gather -> fold of the lower ranks' totals, all on the device
         total = ops.reduce(op, src)[0]  # rb200_reduce_kind SUM/MIN/MAX == rb200_op PLUS/MINIMUM/MAXIMUM
         if rng.comm is not None and getattr(ops, "res", None) is not None:
-            totals = rng.comm.allgather_small(total, ops.res).reshape(rng.world)
+            # the fold of the lower ranks' totals comes out of the exchange kernel itself
+            carry = rng.comm.allreduce_small(total, op, ops.res, exclusive_prefix=True)
+            if rng.rank == 0:
+                carry = None
         else:
             totals = torch.empty(rng.world, dtype=src.dtype, device=src.device)
             dist.all_gather_into_tensor(totals, total, group=rng.group)
-        lower = totals[:rng.rank]
-        if rng.rank == 0:
-            carry = None
-        else:
-            carry = _fold(op, lower).reshape(1).contiguous()
+            lower = totals[:rng.rank]
+            carry = None if rng.rank == 0 else _fold(op, lower).reshape(1).contiguous()
     ops.scan(inclusive, op, src, dst, init, carry)
 
 
@@ -379,6 +415,17 @@ def sort_pairs(rng, keys, vals=None, descending=False, ops=None, res=None, keys_
     if W - 1 > 7:
         raise ValueError("sort_pairs: at most 8 ranks (one node)")
     dev, kdt = keys.device, keys.dtype
+    comm = rng.comm if getattr(ops, "res", None) is not None else None
+    if comm is not None:
+        # everything up to the local sort inside the library, on the stream: samples all-gathered through peer memory,
+        # splitters selected on the device, fused partition + all-to-all; one host sync (the received count)
+        got = _peer_sample_exchange(comm, keys, vals, min(W * oversample, 4096), descending, ops.res)
+        if got is not None:
+            keys_out, vals_out = got
+            ops.sort_pairs(keys_out, vals_out, descending, keys_alt if keys_alt is not None and keys_alt.numel() >= keys_out.numel() else None,
+                           vals_alt if vals_alt is not None and vals_out is not None and vals_alt.numel() >= vals_out.numel() else None)
+            return keys_out, vals_out
+        # some rank's share exceeds its receive buffer (the decision is the same on every rank): collective path below
     kview = _signed_view(keys)
     # regular sample of the unsorted shard: [count, samples ...] travels in ONE all-gather (count <= W * oversample is exact in
     # every key type), invalid slots sort behind everything through a sentinel, so the only host sync is the splitters' D2H
@@ -414,13 +461,6 @@ def sort_pairs(rng, keys, vals=None, descending=False, ops=None, res=None, keys_
     if kdt in _SIGNED:
         splitters = splitters.view({torch.uint32: "uint32", torch.uint64: "uint64"}[kdt])
     # a key goes to the rank given by the number of splitters that sort at or before it
-    comm = rng.comm if getattr(ops, "res", None) is not None else None
-    if comm is not None and comm.capacity(keys.element_size(), vals.element_size() if vals is not None else 0) >= n + n // 8:
-        # fused partition + all-to-all: the splitter sweep stores every bucket into its destination GPU
-        keys_out, vals_out = comm.exchange_pairs(keys, vals, splitters, descending, ops.res)
-        ops.sort_pairs(keys_out, vals_out, descending, keys_alt if keys_alt is not None and keys_alt.numel() >= keys_out.numel() else None,
-                       vals_alt if vals_alt is not None and vals_out is not None and vals_alt.numel() >= vals_out.numel() else None)
-        return keys_out, vals_out
     kpart, vpart, bucket_counts = ops.partition_pairs(keys, vals, splitters, descending, keys_alt, vals_alt)
     send_counts = bucket_counts[:W].to(torch.int64).contiguous()
     recv_counts = torch.empty_like(send_counts)

@@ -106,6 +106,22 @@ for r, dt in (("ReduceSum", "CoreReductionDataTypeList"), ("ReduceMin", "CoreRed
     suite(f"launch-basic-param-expt-{r}", D + "test-launch-basic-param-expt-reduce.cpp.in", dict(BACKEND="B200", REDUCETYPE=r, DATATYPES=dt),
           inject={'#include "RAJA_test-launch-execpol.hpp"': LAUNCH_LISTS})
 
+# ---- kernel / reduce-params: RAJA::kernel_param with expt::Reduce / ReduceLoc parameters (the four loop nests of the CUDA list)
+KERNEL_LISTS = """
+using B200KernelLocExecPols =
+  camp::list<
+    RAJA::KernelPolicy<RAJA::statement::B200Kernel<RAJA::statement::For<1, RAJA::cuda_thread_x_loop, RAJA::statement::For<0, RAJA::cuda_thread_y_loop, RAJA::statement::Lambda<0>>>>>,
+    RAJA::KernelPolicy<RAJA::statement::For<1, RAJA::seq_exec, RAJA::statement::B200Kernel<RAJA::statement::For<0, RAJA::cuda_thread_x_loop, RAJA::statement::Lambda<0>>>>>,
+    RAJA::KernelPolicy<RAJA::statement::B200Kernel<RAJA::statement::For<1, RAJA::seq_exec, RAJA::statement::For<0, RAJA::cuda_thread_x_loop, RAJA::statement::Lambda<0>>>>>,
+    RAJA::KernelPolicy<RAJA::statement::B200Kernel<RAJA::statement::For<1, RAJA::cuda_thread_x_loop, RAJA::statement::For<0, RAJA::seq_exec, RAJA::statement::Lambda<0>>>>>,
+    RAJA::KernelPolicy<RAJA::statement::B200KernelFixed<256, RAJA::statement::For<1, RAJA::cuda_block_x_loop, RAJA::statement::For<0, RAJA::cuda_thread_x_loop, RAJA::statement::Lambda<0>>>>>
+  >;
+using B200KernelLocReducePols = camp::list<RAJA::b200_reduce>;
+using B200KernelLocForallPols = camp::list<RAJA::b200_exec<1024, true>>;
+"""
+suite("kernel-basic-param", "functional/kernel/reduce-params/test-kernel-basic-param.cpp.in", dict(LOC_BACKEND="B200"),
+      inject={'#include "test-kernel-basic-param.hpp"': KERNEL_LISTS})
+
 # ---- workgroup (functional): ordered / reverse_ordered / fused unordered runners, three storage policies, dispatchers
 WG_LISTS = """
 using B200ExecPolicyList = camp::list<RAJA::b200_work<1024>, RAJA::b200_work<256>>;
@@ -173,8 +189,11 @@ libgtest.a:
 """)
     for name, out, incs in rules:
         inc = " ".join("-I" + i for i in incs)
-        mk.append(f"obj/{name}.o: {out} $(DEPS)\n\t@mkdir -p obj\n\t$(NVCC) $(FLAGS) {inc} -x cu -c {out} -o $@\n"
-                  f"bin/{name}: obj/{name}.o libgtest.a $(REFLIB)\n\t@mkdir -p bin\n\t$(NVCC) $(ARCH) -ccbin /usr/bin/g++ obj/{name}.o libgtest.a $(REFLIB) $(LIBS) -o $@\n")
+        # compile, link, strip and drop the object: the objects would triple the snapshot that travels to the GPU box
+        mk.append(f"bin/{name}: {out} libgtest.a $(REFLIB) $(DEPS)\n\t@mkdir -p bin obj\n"
+                  f"\t$(NVCC) $(FLAGS) {inc} -x cu -c {out} -o obj/{name}.o\n"
+                  f"\t$(NVCC) $(ARCH) -ccbin /usr/bin/g++ obj/{name}.o libgtest.a $(REFLIB) $(LIBS) -o $@\n"
+                  f"\t@strip $@; rm -f obj/{name}.o\n")
     mk.append(".PHONY: all\n")
     path = os.path.join(BUILD, "Makefile")
     text = "\n".join(mk)

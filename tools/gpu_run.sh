@@ -1,0 +1,24 @@
+#!/bin/bash
+# tools/gpu_run.sh WHAT...  -- run on the GPU box (via gpurun); writes everything under gpurun_out/<tag>/
+#   tests     pytest -m gpu (everything)          bench     python bench.py (short)
+#   refsuite  only tests/test_refsuite.py          adapter   only tests/test_raja_adapter.py
+#   ncu-list  launch list of one bench step        paths     tools/run_path.py table
+TAG=${TAG:-r02}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
+for what in "$@"; do
+  case $what in
+    tests)    timeout 2400 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.txt 2>&1; echo "tests rc=$?" ;;
+    tests-all) timeout 2400 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.txt 2>&1; echo "tests rc=$?" ;;
+    refsuite) timeout 2400 python -m pytest tests/test_refsuite.py -m gpu -q > $OUT/pytest_refsuite.txt 2>&1; echo "refsuite rc=$?" ;;
+    adapter)  timeout 1200 python -m pytest tests/test_raja_adapter.py -m gpu -q > $OUT/pytest_adapter.txt 2>&1; echo "adapter rc=$?" ;;
+    parity)   timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -q > $OUT/pytest_parity.txt 2>&1; echo "parity rc=$?" ;;
+    smoke)    timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.txt 2>&1; echo "smoke rc=$?" ;;
+    bench)    timeout 900 python bench.py --steps ${STEPS:-10} --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -c 3000 $OUT/bench.json ;;
+    bench-ref) timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; echo "bench-ref rc=$?" ;;
+    ncu-list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-verify --no-reference-gpu > $OUT/ncu_bench.log 2>&1; echo "ncu-list rc=$?" ;;
+    paths)    timeout 900 python tools/run_path.py > $OUT/paths.txt 2>&1; echo "paths rc=$?" ;;
+    *)        echo "running: $what"; timeout 1800 bash -c "$what" > $OUT/cmd_$(date +%s).txt 2>&1; echo "rc=$?" ;;
+  esac
+done

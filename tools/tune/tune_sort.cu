@@ -138,11 +138,16 @@ int main(int argc, char** argv)
   run_shape<rsort::SweepShape<256, 30, 4, 3, false, 300>>(b);
   run_shape<rsort::SweepShape<256, 24, 4, 3, false, 400>>(b);
 #elif TK == 2
-  run_shape<rsort::SweepShape<384, 16, 2, 2>>(b);
-  run_shape<rsort::SweepShape<256, 16, 3, 3, false, 300>>(b);
-  run_shape<rsort::SweepShape<256, 18, 3, 3, false, 300>>(b);
-  run_shape<rsort::SweepShape<384, 16, 2, 3, false, 200>>(b);
-  run_shape<rsort::SweepShape<256, 14, 4, 3, false, 400>>(b);
+  // r02: 64-bit keys move twice the bytes per key, so the r01 shapes (4608-key tiles) pay the per-tile costs (look-back,
+  // barriers) twice as often per byte as the u32 pairs; larger tiles at 2 CTAs per SM
+  run_shape<rsort::SweepShape<256, 18, 3, 3, false, 300, 2, 2>>(b);
+  run_shape<rsort::SweepShape<256, 24, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<256, 28, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<256, 32, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<384, 20, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<384, 22, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<512, 16, 1, 3, false, 150, 2, 2>>(b);
+  run_shape<rsort::SweepShape<512, 24, 1, 3, false, 150, 2, 2>>(b);
 #elif TK == 3
   run_shape<rsort::SweepShape<384, 12, 2, 2>>(b);
   run_shape<rsort::SweepShape<256, 16, 3, 3, false, 300>>(b);
