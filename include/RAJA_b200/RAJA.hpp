@@ -10,6 +10,7 @@
 //     RAJA::b200_synchronize
 //     RAJA::b200_launch_t<Async>            (RAJA::launch, with or without expt::Reduce params)
 //     RAJA::statement::B200Kernel<...>      (RAJA::kernel / kernel_param, with or without expt::Reduce params)
+//     RAJA::b200_multi_exec<BLOCK, Async>   (sharded forall / reducer params / scans across the GPUs of one node; RAJA::b200::MultiResource)
 //     RAJA::b200_work<BLOCK, Async>, RAJA::unordered_b200_fused   (WorkPool / WorkGroup / WorkSite)
 //     RAJA::b200::{device,device_zeroed,pinned}_mempool_type
 //
@@ -83,5 +84,6 @@
 #include "RAJA_b200/launch.hpp"
 #include "RAJA_b200/kernel.hpp"
 #include "RAJA_b200/workgroup.hpp"
+#include "RAJA_b200/multi.hpp"
 
 #endif  // RAJA_B200_RAJA_HPP

@@ -22,6 +22,10 @@ struct LaunchInfo
   cudaStream_t stream;
   RAJA::resources::Cuda res;
 
+  // non-null for a b200_multi_exec launch: every reducer result is all-gathered over the ranks before it is fetched
+  rb200_comm_t comm = RAJA::b200_detail::tl_multi_launch_comm();
+  int world         = comm ? RAJA::b200_detail::tl_multi().world : 1;
+
   static constexpr int max_results = 16;
   struct Result
   {
@@ -40,7 +44,7 @@ struct LaunchInfo
     if (n_results < max_results)
     {
       results[n_results++] = Result {dev, (unsigned)bytes, staged};
-      staged += (unsigned)((bytes + 15) & ~size_t(15));
+      staged += (unsigned)(((bytes + 15) & ~size_t(15)) * (size_t)world);  // multi launch: one copy per rank, rank order
     }
   }
   // param_resolve: host copy of the result at `dev` (valid until this LaunchInfo is destroyed)
@@ -50,23 +54,47 @@ struct LaunchInfo
     {
       staging = rb200_pinned_malloc(staged);
       if (!staging) throw std::runtime_error(std::string("raja_b200: reducer staging: ") + rb200_last_error());
-      for (int i = 0; i < n_results; ++i)
-        RAJA::b200_detail::check(cudaMemcpyAsync(static_cast<char*>(staging) + results[i].offset, results[i].dev, results[i].bytes,
-                                                 cudaMemcpyDeviceToHost, stream),
-                                 "reducer readback");
+      if (comm)
+      {
+        // all ranks' results of every reducer, gathered through peer memory in rank order (one small kernel each)
+        gathered = rb200_device_malloc(staged, stream);
+        if (!gathered) throw std::runtime_error(std::string("raja_b200: reducer staging: ") + rb200_last_error());
+        for (int i = 0; i < n_results; ++i)
+          RAJA::b200_detail::check_rc(rb200_comm_allgather_small(comm, results[i].dev, (int)stride(i), static_cast<char*>(gathered) + results[i].offset, stream),
+                                      "reducer all-gather");
+        RAJA::b200_detail::check(cudaMemcpyAsync(staging, gathered, staged, cudaMemcpyDeviceToHost, stream), "reducer readback");
+      }
+      else
+      {
+        for (int i = 0; i < n_results; ++i)
+          RAJA::b200_detail::check(cudaMemcpyAsync(static_cast<char*>(staging) + results[i].offset, results[i].dev, results[i].bytes,
+                                                   cudaMemcpyDeviceToHost, stream),
+                                   "reducer readback");
+      }
       RAJA::b200_detail::check(cudaStreamSynchronize(stream), "reducer readback");
       fetched = true;
     }
     for (int i = 0; i < n_results; ++i)
       if (results[i].dev == dev) return static_cast<char*>(staging) + results[i].offset;
+    if (comm) throw std::runtime_error("raja_b200: a b200_multi_exec launch takes at most 16 reducer parameters");
     // more reducers than slots: fetch this one on its own
     if (!overflow) overflow = rb200_pinned_malloc(64);
     RAJA::b200_detail::check(cudaMemcpyAsync(overflow, dev, bytes, cudaMemcpyDeviceToHost, stream), "reducer readback");
     RAJA::b200_detail::check(cudaStreamSynchronize(stream), "reducer readback");
     return overflow;
   }
+  // bytes between the copies of two ranks' results of reducer i (multi launch)
+  size_t stride(int i) const { return (results[i].bytes + 15) & ~size_t(15); }
+  size_t stride_of(const void* dev) const
+  {
+    for (int i = 0; i < n_results; ++i)
+      if (results[i].dev == dev) return stride(i);
+    return 0;
+  }
+  void* gathered = nullptr;
   ~LaunchInfo()
   {
+    if (gathered) rb200_device_free(gathered, stream);
     if (staging) rb200_pinned_free(staging);
     if (overflow) rb200_pinned_free(overflow);
   }
@@ -121,8 +149,9 @@ forall_impl(resources::Cuda res, b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async
   Iterator end        = std::end(iter);
   const IndexType len = std::distance(begin, end);
 
-  // only launch if there is something to iterate over (policy/cuda/forall.hpp:598)
-  if (len > 0)
+  // only launch if there is something to iterate over (policy/cuda/forall.hpp:598) -- except that a rank with an empty shard
+  // still takes part in the exchange of a multi-GPU launch's reducer results (it contributes the identity)
+  if (len > 0 || (!empty && RAJA::b200_detail::tl_multi_launch_comm() != nullptr))
   {
     cudaStream_t stream = res.get_stream();
     // b200_exec_grid<BLOCK, GRID>: the caller's grid (never more blocks than units of work); otherwise SMs x resident CTAs
@@ -148,6 +177,21 @@ forall_impl(resources::Cuda res, b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async
     if (!Async) res.wait();
   }
   return resources::EventProxy<resources::Cuda>(res);
+}
+
+// b200_multi_exec: the same launch on this rank's shard; the reducer parameters of the launch are combined over the ranks
+// in param_resolve (LaunchInfo::comm is picked up from the guard below)
+template<typename Iterable, typename LoopBody, size_t BLOCK_SIZE, bool Async, typename ForallParam>
+RAJA_INLINE concepts::enable_if_t<resources::EventProxy<resources::Cuda>, RAJA::expt::type_traits::is_ForallParamPack<ForallParam>>
+forall_impl(resources::Cuda res, b200_multi_exec<BLOCK_SIZE, Async> const&, Iterable&& iter, LoopBody&& loop_body, ForallParam f_params)
+{
+  const RAJA::b200_detail::MultiState& m = RAJA::b200_detail::multi_state_or_throw("forall<b200_multi_exec>");
+  struct Guard
+  {
+    explicit Guard(rb200_comm_t c) { RAJA::b200_detail::tl_multi_launch_comm() = c; }
+    ~Guard() { RAJA::b200_detail::tl_multi_launch_comm() = nullptr; }
+  } guard(m.world > 1 ? m.comm : nullptr);
+  return forall_impl(res, b200_exec_explicit<BLOCK_SIZE, 0, Async> {}, std::forward<Iterable>(iter), std::forward<LoopBody>(loop_body), f_params);
 }
 
 // RAJA::synchronize<b200_synchronize>() (policy/cuda/synchronize.hpp:39-42)

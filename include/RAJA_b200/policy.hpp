@@ -34,6 +34,16 @@ struct b200_exec_explicit
 template<size_t BLOCK_SIZE, bool Async = false>
 using b200_exec = b200_exec_explicit<BLOCK_SIZE, 0, Async>;
 
+// Multi-GPU range policy: the calling rank -- one process, or one host thread per device -- owns a
+// contiguous shard of the global iteration space; kernels run on the shard, and only the paths with a real exchange step
+// talk to the other GPUs, through the peer-memory communicator of libraja_b200.so (rb200_comm_*): reducer results are
+// all-gathered and folded in rank order, a scan gets the fold of the lower ranks' totals as its carry, a sort is a sample
+// sort with a fused partition + all-to-all.  The rank's communicator is the one made current by RAJA::b200::MultiResource
+// (RAJA_b200/multi.hpp) on this host thread.  Everything a b200_exec does, it does the same way (it IS one).
+template<size_t BLOCK_SIZE, bool Async = false>
+struct b200_multi_exec : public b200_exec_explicit<BLOCK_SIZE, 0, Async>
+{};
+
 // classic reducer objects (policy/cuda/policy.hpp:1550-1620).  Ordered: last-block-done over the grid's partials in fixed
 // slot order (run-to-run deterministic).  Unordered ("atomic"): one device atomic per block on a self-resetting slot;
 // value types / operators the ISA has no atomic for fall back to the ordered combine, as the reference's atomic
@@ -67,6 +77,7 @@ using policy::b200::b200_atomic;
 using policy::b200::b200_atomic_explicit;
 using policy::b200::b200_exec;
 using policy::b200::b200_exec_explicit;
+using policy::b200::b200_multi_exec;
 using policy::b200::b200_reduce;
 using policy::b200::b200_reduce_atomic;
 using policy::b200::b200_reduce_base;
@@ -87,10 +98,42 @@ struct get_resource<::RAJA::policy::b200::b200_exec_explicit<BLOCK_SIZE, GRID_SI
 {
   using type = camp::resources::Cuda;
 };
+template<size_t BLOCK_SIZE, bool Async>
+struct get_resource<::RAJA::policy::b200::b200_multi_exec<BLOCK_SIZE, Async>>
+{
+  using type = camp::resources::Cuda;
+};
 }  // namespace resources
 
 namespace b200_detail
 {
+// the rank this host thread acts as (set by RAJA::b200::MultiResource::make_current)
+struct MultiState
+{
+  rb200_comm_t comm = nullptr;
+  int rank          = 0;
+  int world         = 1;
+  size_t ws_bytes   = 0;
+  char* ws          = nullptr;  // this rank's own workspace (receive buffers of the sort live there)
+};
+inline MultiState& tl_multi()
+{
+  static thread_local MultiState s;
+  return s;
+}
+// non-null while a b200_multi_exec launch is being set up on this thread: the launch's reducer results are combined across ranks
+inline rb200_comm_t& tl_multi_launch_comm()
+{
+  static thread_local rb200_comm_t c = nullptr;
+  return c;
+}
+inline const MultiState& multi_state_or_throw(const char* what)
+{
+  const MultiState& m = tl_multi();
+  if (m.comm == nullptr) throw std::runtime_error(std::string("raja_b200: ") + what + ": no RAJA::b200::MultiResource is current on this thread");
+  return m;
+}
+
 inline void check(cudaError_t e, const char* what)
 {
   if (e != cudaSuccess) throw std::runtime_error(std::string("raja_b200: ") + what + ": " + cudaGetErrorString(e));

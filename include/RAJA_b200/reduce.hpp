@@ -232,8 +232,15 @@ inline void resolve(Red& red, ::RAJA::policy::b200::LaunchInfo& li)
 {
   using T = typename Red::value_type;
   alignas(alignof(T)) unsigned char raw[sizeof(T)];
-  memcpy(raw, li.fetch(red.devicetarget, sizeof(T)), sizeof(T));
-  red.combineTarget(*reinterpret_cast<T*>(raw));
+  const char* host = static_cast<const char*>(li.fetch(red.devicetarget, sizeof(T)));
+  // one value per rank for a b200_multi_exec launch, folded into the target in rank order (deterministic; ranks own
+  // ascending index ranges, so a location reducer keeps the first extremum)
+  const size_t stride = li.comm ? li.stride_of(red.devicetarget) : 0;
+  for (int r = 0; r < (li.comm ? li.world : 1); ++r)
+  {
+    memcpy(raw, host + (size_t)r * stride, sizeof(T));
+    red.combineTarget(*reinterpret_cast<T*>(raw));
+  }
   rb200_device_zeroed_free(red.device_count, li.stream);
   red.device_count = nullptr;
   rb200_device_free(red.devicetarget, li.stream);

@@ -94,6 +94,22 @@ inline resources::EventProxy<resources::Cuda> stable_pairs(resources::Cuda res, 
   return b200_detail::sort_pairs<Async>(res, kb, ke, vb, comp);
 }
 
+
+// b200_multi_exec: a sharded sort returns a piece of data-dependent size, which the in-place RAJA::sort signature cannot express
+template<typename> struct multi_sort_not_in_place : std::false_type {};
+#define RAJA_B200_NO_MULTI_SORT(NAME, ...)                                                                                          \
+  template<size_t BLOCK_SIZE, bool Async, typename Iter, typename... Rest>                                                         \
+  inline resources::EventProxy<resources::Cuda> NAME(resources::Cuda res, ::RAJA::policy::b200::b200_multi_exec<BLOCK_SIZE, Async> const&, Iter, Rest...) \
+  {                                                                                                                                 \
+    static_assert(multi_sort_not_in_place<Iter>::value, "RAJA::sort with b200_multi_exec: use RAJA::b200::multi_sort_pairs / multi_sort (RAJA_b200/multi.hpp)"); \
+    return resources::EventProxy<resources::Cuda>(res);                                                                             \
+  }
+RAJA_B200_NO_MULTI_SORT(unstable)
+RAJA_B200_NO_MULTI_SORT(stable)
+RAJA_B200_NO_MULTI_SORT(unstable_pairs)
+RAJA_B200_NO_MULTI_SORT(stable_pairs)
+#undef RAJA_B200_NO_MULTI_SORT
+
 }  // namespace sort
 }  // namespace impl
 }  // namespace RAJA

@@ -499,8 +499,27 @@ inline cudaError_t launch(cudaStream_t stream, const T* in, T* out, long long n,
     // grid fits, e.g. after another scan on another stream has drained) and fails instead of hanging when it cannot.
     unsigned* ticket = (unsigned*)workspace;
     void* args[] = {(void*)&in, (void*)&out, (void*)&n, (void*)&init, (void*)&carry_dev, (void*)&ts, (void*)&ticket, (void*)&flags, (void*)&trace};
-    return cudaLaunchCooperativeKernel((const void*)scan_kernel<T, Op, Inclusive, S>, dim3((unsigned)grid), dim3(S::THREADS), args,
-                                       Layout<T, S>::SMEM_BYTES, stream);
+    const void* kern = (const void*)scan_kernel<T, Op, Inclusive, S>;
+    e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(S::THREADS), args, Layout<T, S>::SMEM_BYTES, stream);
+    if (e != cudaErrorCooperativeLaunchTooLarge) return e;
+    // The driver finds fewer co-resident CTAs than the cached occupancy promised (another context or runtime instance holds
+    // part of the shared-memory carve-out, a smaller MPS partition, ...): ask again, now, and shrink the grid -- any grid
+    // works, a CTA simply owns more tiles.  The workspace is still zero: the refused launch never ran.
+    cudaGetLastError();
+    int occ_now = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_now, scan_kernel<T, Op, Inclusive, S>, S::THREADS, Layout<T, S>::SMEM_BYTES) == cudaSuccess) {
+      const long long g = (long long)device_info().sm_count * occ_now;
+      if (occ_now > 0 && g < grid) {
+        e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)g), dim3(S::THREADS), args, Layout<T, S>::SMEM_BYTES, stream);
+        if (e != cudaErrorCooperativeLaunchTooLarge) return e;
+        cudaGetLastError();
+      }
+    }
+    // no cooperative launch possible on this device / context although the occupancy query says the grid fits: a plain launch, which is safe whenever the grid does
+    // become fully resident (always on an otherwise idle GPU); the bounded look-back spin turns the other case into an error
+    scan_kernel<T, Op, Inclusive, S><<<(unsigned)grid, S::THREADS, Layout<T, S>::SMEM_BYTES, stream>>>(in, out, n, init, carry_dev, ts, (unsigned*)workspace, flags,
+                                                                                                        trace);
+    return cudaGetLastError();
   }
   // one tile per CTA: a tile only looks back at lower tickets, i.e. at CTAs that have already started
   scan_kernel<T, Op, Inclusive, S><<<(unsigned)grid, S::THREADS, Layout<T, S>::SMEM_BYTES, stream>>>(in, out, n, init, carry_dev, ts,

@@ -9,12 +9,12 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 BUILD = os.path.join(HERE, "cpp", "_build")
-PROGRAMS = ["test_forall_reduce", "test_scan_sort_atomic", "test_multi_reduce", "test_launch_reduce", "test_workgroup"]
+PROGRAMS = ["test_forall_reduce", "test_scan_sort_atomic", "test_multi_reduce", "test_launch_reduce", "test_workgroup", "test_multi"]
 
 
 def test_adapter_headers_present():
     inc = os.path.join(os.path.dirname(HERE), "include", "RAJA_b200")
-    for h in ("RAJA.hpp", "policy.hpp", "pools.hpp", "forall.hpp", "reduce.hpp", "reduce_classic.hpp", "scan.hpp", "sort.hpp", "atomic.hpp", "multi_reduce.hpp", "launch.hpp", "workgroup.hpp"):
+    for h in ("RAJA.hpp", "policy.hpp", "pools.hpp", "forall.hpp", "reduce.hpp", "reduce_classic.hpp", "scan.hpp", "sort.hpp", "atomic.hpp", "multi_reduce.hpp", "launch.hpp", "workgroup.hpp", "kernel.hpp", "indexset.hpp", "multi.hpp"):
         assert os.path.exists(os.path.join(inc, h)), h
 
 

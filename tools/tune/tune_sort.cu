@@ -146,18 +146,23 @@ int main(int argc, char** argv)
   run_shape<rsort::SweepShape<256, 32, 2, 3, false, 200, 2, 2>>(b);
   run_shape<rsort::SweepShape<384, 20, 2, 3, false, 200, 2, 2>>(b);
   run_shape<rsort::SweepShape<384, 22, 2, 3, false, 200, 2, 2>>(b);
-  run_shape<rsort::SweepShape<512, 16, 1, 3, false, 150, 2, 2>>(b);
-  run_shape<rsort::SweepShape<512, 24, 1, 3, false, 150, 2, 2>>(b);
+  run_shape<rsort::SweepShape<384, 24, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<384, 26, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<256, 36, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<512, 16, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<512, 18, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<384, 22, 2, 3, false, 300, 2, 2>>(b);
+  run_shape<rsort::SweepShape<384, 22, 2, 3, false, 120, 2, 2>>(b);
 #elif TK == 3
-  run_shape<rsort::SweepShape<384, 12, 2, 2>>(b);
-  run_shape<rsort::SweepShape<256, 16, 3, 3, false, 300>>(b);
-  run_shape<rsort::SweepShape<256, 14, 3, 3, false, 300>>(b);
-  run_shape<rsort::SweepShape<384, 14, 2, 3, false, 200>>(b);
+  run_shape<rsort::SweepShape<256, 16, 3, 3, false, 300, 2, 2>>(b);
+  run_shape<rsort::SweepShape<256, 24, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<384, 16, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<384, 18, 2, 3, false, 200, 2, 2>>(b);
 #elif TK == 4
-  run_shape<rsort::SweepShape<384, 12, 2, 2>>(b);
-  run_shape<rsort::SweepShape<256, 14, 3, 3, false, 300>>(b);
-  run_shape<rsort::SweepShape<256, 12, 3, 3, false, 300>>(b);
-  run_shape<rsort::SweepShape<384, 12, 2, 3, false, 200>>(b);
+  run_shape<rsort::SweepShape<256, 14, 3, 3, false, 300, 2, 2>>(b);
+  run_shape<rsort::SweepShape<256, 20, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<384, 14, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<384, 16, 2, 3, false, 200, 2, 2>>(b);
 #else
   run_shape<rsort::SweepShape<384, 16, 2, 2>>(b);
   run_shape<rsort::SweepShape<256, 20, 3, 3, false, 300>>(b);
