@@ -1091,6 +1091,16 @@ template <class U, class VT> struct Tuning {
   static constexpr int ITEMS = sizeof(U) == 4 ? (VB <= 4 ? 32 : 20) : (VB == 0 ? 18 : (VB == 4 ? 16 : 14));
   using shape = SweepShape<256, ITEMS, 3, 3, false, 300, 2, 2>;
 };
+// 64-bit keys move twice the bytes per key: with the 3-CTA shapes a tile holds only 4-4.6 K keys and the per-tile costs
+// (look-back round trips, barriers) are paid twice as often per byte as for the u32 pairs.  Larger tiles at 2 CTAs per SM
+// (r02 sweep, profiles/r02_sort_tuning.txt): keys only 10.89 -> 9.85 ms at 2^28 (384 x 26 = 9984 keys per tile),
+// u64 + 4-byte values 13.90 -> 12.99 ms (384 x 18); u64 + 8-byte values is flat and keeps the default.
+template <> struct Tuning<unsigned long long, NoValue> {
+  using shape = SweepShape<384, 26, 2, 3, false, 200, 2, 2>;
+};
+template <> struct Tuning<unsigned long long, uint32_t> {
+  using shape = SweepShape<384, 18, 2, 3, false, 200, 2, 2>;
+};
 
 template <class U, class VT, class S = typename Tuning<U, VT>::shape> inline long long num_tiles(long long n)
 {

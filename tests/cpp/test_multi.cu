@@ -37,7 +37,11 @@ static void rank_main(int rank, int world, RAJA::b200::LocalPeerGroup* group, Co
 {
   CK(cudaSetDevice(rank % [] { int n = 1; cudaGetDeviceCount(&n); return n; }()));
   void* const* ptrs = group->attach(rank);
-  RAJA::resources::Cuda res;
+  // camp's default Cuda resource draws from a stream pool created on whichever device was current first: a rank that owns
+  // another device brings its own stream (camp::resources::Cuda::CudaFromStream, tpl/camp/include/camp/resource/cuda.hpp:140-146)
+  cudaStream_t stream;
+  CK(cudaStreamCreate(&stream));
+  RAJA::resources::Cuda res = RAJA::resources::Cuda::CudaFromStream(stream);
   RAJA::b200::MultiResource mres(rank, world, ptrs, group->bytes(), res);
 
   // ---- global data, the same on every rank (each rank uploads only its shard)

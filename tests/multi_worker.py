@@ -131,7 +131,9 @@ def main():
 
     checks = 0
     # on GPUs every path runs twice: exchanges by NCCL collectives, then over the NVLink peer-memory communicator
-    comms = [None, multi.PeerComm(exchange_bytes=32 << 20)] if cuda else [None]
+    # (the third communicator's receive buffers are too small for the largest size: the sort must fall back, on every rank
+    # alike, to the collective all-to-all)
+    comms = [None, multi.PeerComm(exchange_bytes=32 << 20), multi.PeerComm(exchange_bytes=2 << 20)] if cuda else [None]
     for comm, n_global in [(c, n) for c in comms for n in ((0, 1, 5, 1000, 20011) if not cuda else (5, 1000, 1 << 20))]:
         rng_np = np.random.default_rng(1234 + n_global)  # same stream on every rank
         sr = multi.ShardedRange.split(n_global, world, rank)

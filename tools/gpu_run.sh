@@ -18,6 +18,15 @@ for what in "$@"; do
     bench)    timeout 900 python bench.py --steps ${STEPS:-10} --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -c 3000 $OUT/bench.json ;;
     bench-ref) timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; echo "bench-ref rc=$?" ;;
     ncu-list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-verify --no-reference-gpu > $OUT/ncu_bench.log 2>&1; echo "ncu-list rc=$?" ;;
+    multi-cpp) timeout 600 tests/cpp/_build/test_multi > $OUT/test_multi_world${GPUS:-2}.txt 2>&1; echo "multi-cpp rc=$?"; tail -3 $OUT/test_multi_world${GPUS:-2}.txt ;;
+    multi-py) timeout 900 python -m pytest tests/test_multi_gloo.py -m gpu -q > $OUT/pytest_multi_gpu.txt 2>&1; echo "multi-py rc=$?"; tail -3 $OUT/pytest_multi_gpu.txt ;;
+    bench-n)  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${GPUS:-2} --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus ${GPUS:-2} --steps ${STEPS:-10} --warmup 3 > $OUT/bench_n${GPUS:-2}.json 2> $OUT/bench_n${GPUS:-2}.err; echo "bench-n rc=$?"; tail -c 1500 $OUT/bench_n${GPUS:-2}.json; tail -5 $OUT/bench_n${GPUS:-2}.err ;;
+    bench-n-nccl) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${GPUS:-2} --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus ${GPUS:-2} --steps ${STEPS:-10} --warmup 3 --nccl-exchange --no-e2e > $OUT/bench_n${GPUS:-2}_nccl.json 2> $OUT/bench_n${GPUS:-2}_nccl.err; echo "bench-n-nccl rc=$?"; tail -c 600 $OUT/bench_n${GPUS:-2}_nccl.json ;;
+    sanitize) for t in forall-basic-ReduceSum forall-basic-expt-ReduceMinLoc forall-segment-multiple-ReduceMaxLoc scan-Inclusive algorithm-stable-sort forall-atomic-basic launch-basic-param-expt-ReduceSum kernel-basic-param reducer-reset resource-MultiStream workgroup-Unordered-Single-Direct; do
+                echo "== memcheck $t"; timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 tests/refsuite/_build/bin/$t --gtest_brief=1 2>&1 | tail -4; done > $OUT/sanitizer_memcheck.txt 2>&1
+              for t in forall-basic-ReduceSum scan-Inclusive kernel-basic-param; do
+                echo "== racecheck $t"; timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 tests/refsuite/_build/bin/$t --gtest_brief=1 2>&1 | tail -4; done > $OUT/sanitizer_racecheck.txt 2>&1
+              echo "sanitize done"; grep -c "ERROR SUMMARY: 0 errors" $OUT/sanitizer_memcheck.txt $OUT/sanitizer_racecheck.txt ;;
     paths)    timeout 900 python tools/run_path.py > $OUT/paths.txt 2>&1; echo "paths rc=$?" ;;
     *)        echo "running: $what"; timeout 1800 bash -c "$what" > $OUT/cmd_$(date +%s).txt 2>&1; echo "rc=$?" ;;
   esac

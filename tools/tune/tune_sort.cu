@@ -127,11 +127,14 @@ int main(int argc, char** argv)
     cudaFree(tmp);
   }
 #if TK == 0
+  // r02: larger tiles at 2 CTAs per SM (what paid for the 64-bit keys)
   run_shape<rsort::SweepShape<256, 32, 3, 3, false, 300, 2, 2>>(b);
-  run_shape<rsort::SweepShape<256, 32, 3, 3, false, 300, 1, 2>>(b);
-  run_shape<rsort::SweepShape<256, 34, 3, 3, false, 300, 1, 2>>(b);
-  run_shape<rsort::SweepShape<256, 32, 3, 3, false, 300, 1, 1>>(b);
-  run_shape<rsort::SweepShape<256, 34, 3, 3, false, 300, 1, 1>>(b);
+  run_shape<rsort::SweepShape<256, 40, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<256, 48, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<384, 28, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<384, 32, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<512, 24, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<512, 20, 2, 3, false, 200, 2, 2>>(b);
 #elif TK == 1
   run_shape<rsort::SweepShape<384, 24, 2, 2>>(b);
   run_shape<rsort::SweepShape<256, 30, 3, 3, false, 300>>(b);
@@ -151,8 +154,11 @@ int main(int argc, char** argv)
   run_shape<rsort::SweepShape<256, 36, 2, 3, false, 200, 2, 2>>(b);
   run_shape<rsort::SweepShape<512, 16, 2, 3, false, 200, 2, 2>>(b);
   run_shape<rsort::SweepShape<512, 18, 2, 3, false, 200, 2, 2>>(b);
-  run_shape<rsort::SweepShape<384, 22, 2, 3, false, 300, 2, 2>>(b);
-  run_shape<rsort::SweepShape<384, 22, 2, 3, false, 120, 2, 2>>(b);
+  run_shape<rsort::SweepShape<384, 28, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<448, 22, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<448, 24, 2, 3, false, 200, 2, 2>>(b);
+  run_shape<rsort::SweepShape<384, 26, 2, 3, false, 200, 2, 2, 400, 12>>(b);
+  run_shape<rsort::SweepShape<384, 26, 2, 3, false, 200, 2, 4>>(b);
 #elif TK == 3
   run_shape<rsort::SweepShape<256, 16, 3, 3, false, 300, 2, 2>>(b);
   run_shape<rsort::SweepShape<256, 24, 2, 3, false, 200, 2, 2>>(b);
