@@ -34,6 +34,15 @@ __global__ void iota_u32(unsigned* p, long n) { for (long i = blockIdx.x * (long
 
 void row(const char* what, const char* pol, double bytes, float ms) { printf("%-34s %-28s %9.4f ms %9.1f GB/s\n", what, pol, ms, bytes / ms / 1e6); fflush(stdout); }
 
+template <class EX, class AP>
+void run_pi_atomic(const char* pol, RAJA::resources::Cuda res, cudaStream_t s, RAJA::TypedRangeSegment<long> seg, double* pi, double dx, long N)
+{
+  float ms = best_ms(s, [&] { cudaMemsetAsync(pi, 0, 8, s); RAJA::forall<EX>(res, seg, [=] RAJA_DEVICE(long i) { double x = (double(i) + 0.5) * dx; RAJA::atomicAdd<AP>(pi, dx / (1.0 + x * x)); }); }, 2, 1);
+  double h = 0;
+  cudaMemcpy(&h, pi, 8, cudaMemcpyDeviceToHost);
+  printf("%-34s %-36s %9.4f ms %9.2f Gupdates/s   pi = %.12f\n", "pi, atomicAdd into one address", pol, ms, N / ms / 1e6, 4.0 * h);
+}
+
 int main(int argc, char** argv)
 {
   const int log2n = argc > 1 ? atoi(argv[1]) : 28;
@@ -118,6 +127,13 @@ int main(int argc, char** argv)
     const int reps = bins == 256 ? 2 : 5;
     row(name, "b200_exec + b200_atomic", 4.0 * N, best_ms(s, [&] { RAJA::forall<B>(res, seg, [=] RAJA_DEVICE(long i) { RAJA::atomicAdd<RAJA::b200_atomic>(&hist[keys[i]], 1); }); }, reps, 1));
     row(name, "cuda_exec + cuda_atomic", 4.0 * N, best_ms(s, [&] { RAJA::forall<C>(res, seg, [=] RAJA_DEVICE(long i) { RAJA::atomicAdd<RAJA::cuda_atomic>(&hist[keys[i]], 1); }); }, reps, 1));
+    // warp-aggregated adds (one atomic per distinct address per warp): pays on contended bins, costs on spread ones
+    row(name, "b200_exec + b200_atomic_aggregated", 4.0 * N, best_ms(s, [&] { RAJA::forall<B>(res, seg, [=] RAJA_DEVICE(long i) { RAJA::atomicAdd<RAJA::b200_atomic_aggregated>(&hist[keys[i]], 1); }); }, reps, 1));
+    // sensitivity of an atomic-bearing body to the block size / grid of the persistent engine
+    row(name, "b200_exec<128> + b200_atomic", 4.0 * N, best_ms(s, [&] { RAJA::forall<RAJA::b200_exec_async<128>>(res, seg, [=] RAJA_DEVICE(long i) { RAJA::atomicAdd<RAJA::b200_atomic>(&hist[keys[i]], 1); }); }, reps, 1));
+    row(name, "b200_exec<512> + b200_atomic", 4.0 * N, best_ms(s, [&] { RAJA::forall<RAJA::b200_exec_async<512>>(res, seg, [=] RAJA_DEVICE(long i) { RAJA::atomicAdd<RAJA::b200_atomic>(&hist[keys[i]], 1); }); }, reps, 1));
+    row(name, "b200_exec<1024> + b200_atomic", 4.0 * N, best_ms(s, [&] { RAJA::forall<RAJA::b200_exec_async<1024>>(res, seg, [=] RAJA_DEVICE(long i) { RAJA::atomicAdd<RAJA::b200_atomic>(&hist[keys[i]], 1); }); }, reps, 1));
+    row(name, "b200_exec_grid<256,296> + b200_atomic", 4.0 * N, best_ms(s, [&] { RAJA::forall<RAJA::b200_exec_grid_async<256, 296>>(res, seg, [=] RAJA_DEVICE(long i) { RAJA::atomicAdd<RAJA::b200_atomic>(&hist[keys[i]], 1); }); }, reps, 1));
     // the same histogram as a MultiReduceSum (the framework-visible form: bins privatised per CTA in shared memory)
     snprintf(name, sizeof name, "MultiReduceSum histogram, %d bins", bins);
     {
@@ -131,6 +147,18 @@ int main(int argc, char** argv)
       RAJA::MultiReduceSum<RAJA::cuda_multi_reduce_atomic, int> mr((size_t)bins);
       row(name, "cuda_exec + cuda_multi_reduce_atomic", 4.0 * N, best_ms(s, [&] { RAJA::forall<C>(res, seg, [=] RAJA_DEVICE(long i) { mr[keys[i]] += 1; }); }, 5, 1));
     }
+  }
+  // ---- pi by atomics (examples/pi-reduce_vs_atomic.cpp: every iteration adds into ONE address) and by a reducer
+  {
+    const long bins = N;
+    const double dx = 1.0 / double(bins);
+    double* pi = c;
+    run_pi_atomic<B, RAJA::b200_atomic>("b200_exec + b200_atomic", res, s, seg, pi, dx, N);
+    run_pi_atomic<B, RAJA::b200_atomic_aggregated>("b200_exec + b200_atomic_aggregated", res, s, seg, pi, dx, N);
+    run_pi_atomic<C, RAJA::cuda_atomic>("cuda_exec + cuda_atomic", res, s, seg, pi, dx, N);
+    double pr = 0;
+    float ms = best_ms(s, [&] { pr = 0; RAJA::forall<B>(res, seg, RAJA::expt::Reduce<RAJA::operators::plus>(&pr), [=] RAJA_DEVICE(long i, RAJA::expt::ValOp<double, RAJA::operators::plus>& p) { double x = (double(i) + 0.5) * dx; p += dx / (1.0 + x * x); }); }, 3, 1);
+    printf("%-34s %-36s %9.4f ms %9.2f Gupdates/s   pi = %.12f\n", "pi, expt::Reduce<plus>", "b200_exec", ms, N / ms / 1e6, 4.0 * pr);
   }
   CK(cudaDeviceSynchronize());
   return 0;
