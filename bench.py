@@ -495,7 +495,8 @@ def run_b200(args):
     lib.rb200_profile_query(b"onesweep_kernel", ctypes.byref(tot), ctypes.byref(cnt))
     pass_ms = tot.value / max(cnt.value, 1)
     kern = {}
-    for name in (b"forall_reduce_kernel", b"forall_kernel", b"scan_kernel", b"histogram_kernel", b"onesweep_kernel"):
+    for name in (b"forall_reduce_kernel", b"forall_kernel", b"scan_kernel", b"histogram_kernel", b"scan_bins_kernel", b"onesweep_kernel", b"bucket_count_kernel",
+                 b"peer_allgather_kernel", b"peer_sample_allgather_kernel", b"pick_splitters_kernel"):
         lib.rb200_profile_query(name, ctypes.byref(tot), ctypes.byref(cnt))
         kern[name.decode()] = {"launches": cnt.value, "avg_ms": tot.value / max(cnt.value, 1), "share_of_step": tot.value / K / step_ms if step_ms else None}
 

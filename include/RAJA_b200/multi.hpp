@@ -152,6 +152,9 @@ inline SortedPiece<K, unsigned> multi_sort(MultiResource& m, const K* keys, long
 
 //! Ranks that are host threads of ONE process: every thread sets its device, then attach()es -- allocates its workspace, enables
 //! peer access to the other devices and learns everyone's pointer.  (Between processes the pointers come from CUDA IPC.)
+//! The exchange kernels wait for their peers ON THE DEVICE: in this one-process mode run with CUDA_MODULE_LOADING=EAGER, so
+//! that no host thread has to synchronise a context (lazy module loading does, at a kernel's first launch) behind a kernel
+//! that is waiting for that very thread's rank.
 class LocalPeerGroup
 {
 public:

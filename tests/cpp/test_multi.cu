@@ -162,6 +162,11 @@ static void rank_main(int rank, int world, RAJA::b200::LocalPeerGroup* group, Co
 
 int main(int argc, char** argv)
 {
+  // Ranks are THREADS of one process here, and the exchange kernels wait for their peers on the device.  With lazy module
+  // loading the first launch of a kernel may have to synchronise the context it is loaded into -- behind a kernel that is
+  // itself waiting for a peer whose host thread is stuck the same way.  Load everything up front.  (One process per GPU,
+  // the deployment mode of bench.py, has one context per process and does not need this.)
+  setenv("CUDA_MODULE_LOADING", "EAGER", 1);
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   int world = ndev < 8 ? ndev : 8;
