@@ -20,6 +20,11 @@ using B200ForallExecPols = camp::list<RAJA::b200_exec<128>,
 using B200ForallReduceExecPols = B200ForallExecPols;
 using B200ForallAtomicExecPols = B200ForallExecPols;
 
+// test/include/RAJA_test-forall-indexset-execpol.hpp:50-54
+using B200ForallIndexSetExecPols = camp::list<RAJA::ExecPolicy<RAJA::seq_segit, RAJA::b200_exec<128>>, RAJA::ExecPolicy<RAJA::seq_segit, RAJA::b200_exec<256>>,
+                                              RAJA::ExecPolicy<RAJA::seq_segit, RAJA::b200_exec_async<256>>>;
+using B200ForallIndexSetReduceExecPols = B200ForallIndexSetExecPols;
+
 // test/include/RAJA_test-forall-async-execpol.hpp
 using B200AsyncForallExecPols = camp::list<RAJA::b200_exec_async<128>, RAJA::b200_exec_async<256>>;
 

@@ -138,6 +138,50 @@ for kind in ("Ordered", "Unordered"):
                   inject={f'#include "test-workgroup-{kind}-': WG_LISTS})
 
 
+# ---- forall / segment, segment-view: the plain loop over the three segment types, every index type, with and without Views
+for seg in ("ListSegment", "RangeSegment", "RangeStrideSegment"):
+    suite(f"forall-{seg}", "functional/forall/segment/test-forall-segment.cpp.in", dict(BACKEND="B200", SEGTYPE=seg))
+for sv in ("ListSegmentView", "RangeSegmentView", "RangeSegment2DView", "RangeStrideSegmentView"):
+    suite(f"forall-{sv}", "functional/forall/segment-view/test-forall-segment-view.cpp.in", dict(BACKEND="B200", SEGVIEWTYPE=sv))
+
+# ---- forall over TypedIndexSets (ExecPolicy<seq_segit, b200_exec>): plain, icount, with Views, with an explicit resource,
+#      with several reducers (the one-wait dispatch of RAJA_b200/indexset.hpp)
+for t in ("IndexSet", "IcountIndexSet"):
+    suite(f"forall-{t}", "functional/forall/indexset/test-forall-indexset.cpp.in", dict(BACKEND="B200", INDEXSETTESTTYPE=t))
+for t in ("IndexSetView", "IcountIndexSetView"):
+    suite(f"forall-{t}", "functional/forall/indexset-view/test-forall-indexset-view.cpp.in", dict(BACKEND="B200", INDEXSETTESTTYPE=t))
+for t in ("ResourceIndexSet", "ResourceIcountIndexSet"):
+    suite(f"forall-{t}", "functional/forall/resource-indexset/test-forall-resource-indexset.cpp.in", dict(BACKEND="B200", INDEXSETTESTTYPE=t))
+for r in ("ReduceSum", "ReduceMin", "ReduceMax", "ReduceMinLoc", "ReduceMaxLoc"):
+    suite(f"forall-indexset-multiple-{r}", "functional/forall/reduce-multiple-indexset/test-forall-indexset-multiple-reduce.cpp.in",
+          dict(BACKEND="B200", REDUCETYPE=r))
+
+# ---- forall / atomic-view: atomics through RAJA::make_atomic_view / MultiView
+for t in ("AtomicView", "AtomicMultiView"):
+    suite(f"forall-{t}", "functional/forall/atomic-view/test-forall-atomic-view.cpp.in", dict(ATOMIC_BACKEND="B200", TEST=t))
+
+# ---- unit / multi_reducer: constructors and reset
+MR_LISTS = """
+using B200MultiReducerPolicyList = camp::list<RAJA::b200_multi_reduce>;
+using B200UnitTestPolicyList = CudaUnitTestPolicyList;  // how ONE device thread runs a test body (forone<test_cuda>), not a back-end
+"""
+suite("multi-reducer-constructors", "unit/multi_reducer/test-multi-reducer-constructors.cpp.in", dict(BACKEND="B200"),
+      inject={'#include "test-multi-reducer-constructors.hpp"': MR_LISTS})
+suite("multi-reducer-reset", "unit/multi_reducer/test-multi-reducer-reset.cpp.in", dict(BACKEND="B200"),
+      inject={'#include "test-multi-reducer-reset.hpp"': MR_LISTS})
+
+# ---- unit / workgroup: constructors, enqueue, dispatcher
+for disp in ("Direct", "IndirectFunction"):
+    suite(f"workgroup-unit-Constructor-{disp}", "unit/workgroup/test-workgroup-Constructor.cpp.in", dict(BACKEND="B200", SUBTESTNAME="Single", DISPATCHER=disp),
+          inject={'#include "test-workgroup-Constructor.hpp"': WG_LISTS})
+    for sub in ("Single", "Multiple"):
+        suite(f"workgroup-unit-Enqueue-{sub}-{disp}", "unit/workgroup/test-workgroup-Enqueue.cpp.in", dict(BACKEND="B200", SUBTESTNAME=sub, DISPATCHER=disp),
+              inject={'#include "test-workgroup-Enqueue-': WG_LISTS})
+    # (unit/workgroup Dispatcher is not instantiated: it drives RAJA::detail::Dispatcher<platform, ...> with the reference's
+    #  internal call signature; the b200 fused runner passes the tile index as a leading call argument, RAJA_b200/workgroup.hpp.
+    #  Dispatch itself is covered by the functional workgroup suites above.)
+
+
 def generate():
     gen = os.path.join(BUILD, "gen")
     os.makedirs(gen, exist_ok=True)
