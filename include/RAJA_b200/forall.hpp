@@ -155,7 +155,12 @@ forall_impl(resources::Cuda res, b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async
   {
     cudaStream_t stream = res.get_stream();
     // b200_exec_grid<BLOCK, GRID>: the caller's grid (never more blocks than units of work); otherwise SMs x resident CTAs
-    int grid = ::b200::forall_grid<(int)BLOCK_SIZE, UNROLL, IndexType, BodyT, FinT>(len, (long long)GRID_SIZE);
+    // User lambdas are opaque.  Without reducers: four waves of CTAs, which lets the block scheduler balance bodies of uneven
+    // cost (atomics: -9 %) and is free for streaming ones (b200/forall.cuh: persistent_grid).  With reducers -- parameters of
+    // the pack, or classic / multi reducer objects that announce themselves while the body is copied below -- one wave: every
+    // CTA pays the block + grid combine (and a multi-reducer its flush), so fewer CTAs are cheaper.
+    constexpr int waves = empty ? 4 : 1;
+    int grid = ::b200::forall_grid<(int)BLOCK_SIZE, UNROLL, IndexType, BodyT, FinT>(len, (long long)GRID_SIZE, waves);
     LaunchInfo info {grid, (int)BLOCK_SIZE, stream, res};
     if constexpr (!empty) RAJA::expt::ParamMultiplexer::parampack_init(pol, f_params, info);
     {
@@ -163,14 +168,18 @@ forall_impl(resources::Cuda res, b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async
       // is copied -- exactly once, inside the scope (RAJA_b200/reduce_classic.hpp); later copies (the
       // by-value kernel argument) just alias that set-up
       size_t dyn_smem = 0;  // what multi-reducers in the body reserved (RAJA_b200/multi_reduce.hpp)
+      int captured    = 0;  // reducer objects captured by the body
       auto make_body = [&]() {
         RAJA::b200_detail::LaunchScope scope(info.grid, stream);
         BodyT b {loop_body, begin, f_params};
         dyn_smem = RAJA::b200_detail::tl_launch().dyn_smem;
+        captured = RAJA::b200_detail::tl_launch().reducers;
         return b;
       };
       BodyT body = make_body();
-      RAJA::b200_detail::check(::b200::launch_forall<(int)BLOCK_SIZE, UNROLL, IndexType>(stream, body, len, FinT {}, info.grid, "forall_kernel", dyn_smem),
+      // the captured reducers sized their scratch for info.grid; a smaller launch just leaves slots unused
+      if (captured > 0 && waves > 1 && GRID_SIZE == 0) grid = ::b200::forall_grid<(int)BLOCK_SIZE, UNROLL, IndexType, BodyT, FinT>(len, 0, 1);
+      RAJA::b200_detail::check(::b200::launch_forall<(int)BLOCK_SIZE, UNROLL, IndexType>(stream, body, len, FinT {}, grid, "forall_kernel", dyn_smem),
                                "forall launch");
     }
     if constexpr (!empty) RAJA::expt::ParamMultiplexer::parampack_resolve(pol, f_params, info);

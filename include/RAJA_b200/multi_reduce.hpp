@@ -143,6 +143,7 @@ struct MultiReduceDataB200
           m_smem_offset = (int)lr.dyn_smem;
           m_smem_repl   = repl;
           lr.dyn_smem += (bin_bytes * repl + 15) & ~size_t(15);
+          ++lr.reducers;  // every CTA flushes its shared bins once: one wave of CTAs (RAJA_b200/forall.hpp)
         }
         else
         {

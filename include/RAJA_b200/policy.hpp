@@ -183,6 +183,7 @@ struct LaunchRecord
   int grid            = 0;
   cudaStream_t stream = 0;
   size_t dyn_smem     = 0;  // dynamic shared memory reserved so far by objects captured in the body (multi-reducers)
+  int reducers        = 0;  // reducer objects (classic, multi) that set themselves up for this launch while the body was copied
 };
 inline LaunchRecord& tl_launch()
 {
@@ -198,6 +199,7 @@ struct LaunchScope
     r.grid     = grid;
     r.stream   = s;
     r.dyn_smem = 0;
+    r.reducers = 0;
   }
   ~LaunchScope() { tl_launch().active = false; }
 };

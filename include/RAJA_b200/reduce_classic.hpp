@@ -90,6 +90,7 @@ public:
         m_kind   = LAUNCH;
         m_parent = nullptr;
         m_stream = lr.stream;
+        ++lr.reducers;
         if (use_atomic)
         {
           m_counter = static_cast<unsigned*>(rb200_device_zeroed_malloc(16, lr.stream));

@@ -87,9 +87,14 @@ forall_kernel(const __grid_constant__ Body body_in, const Index len, const __gri
 
 // Grid size for the persistent mapping: every SM gets its resident CTAs, never
 // more blocks than tiles.
-inline int persistent_grid(int occ_per_sm, long long tiles)
+// `waves` > 1 oversubscribes the device: the hardware block scheduler then hands a fresh CTA to whichever SM frees a slot,
+// which balances loop bodies whose cost is uneven or contended (atomics: a histogram of 2^28 keys into 64 K bins runs at
+// 1.93 ms with one wave at any UNROLL and any number of resident CTAs, 1.77 ms with four waves, 1.70 ms with the reference's one
+// block per 256 indices) and costs streaming bodies nothing (triad 6.60-6.63 TB/s from 1 to 8 waves):
+// profiles/r02_forall_grid_sweep.txt.
+inline int persistent_grid(int occ_per_sm, long long tiles, int waves = 1)
 {
-  long long g = (long long)device_info().sm_count * (occ_per_sm > 0 ? occ_per_sm : 1);
+  long long g = (long long)device_info().sm_count * (occ_per_sm > 0 ? occ_per_sm : 1) * (waves > 0 ? waves : 1);
   if (tiles < 1) tiles = 1;
   if (g > tiles) g = tiles;
   return (int)g;
@@ -110,13 +115,13 @@ inline int forall_occupancy()
 }
 
 template <int BLOCK, int UNROLL, class Index, class Body, class Finalize>
-inline int forall_grid(Index len, long long fixed_grid = 0)
+inline int forall_grid(Index len, long long fixed_grid = 0, int waves = 1)
 {
   // full tiles + the BLOCK-sized chunks of the ragged last tile (each chunk may go to a block of its own)
   const long long tile = (long long)BLOCK * UNROLL, full = (long long)len / tile;
   const long long units = full + ((long long)len - full * tile + BLOCK - 1) / BLOCK;
   if (fixed_grid > 0) return (int)(fixed_grid < units ? fixed_grid : (units < 1 ? 1 : units));  // a grid the caller fixed
-  return persistent_grid(forall_occupancy<BLOCK, UNROLL, Index, Body, Finalize>(), units);
+  return persistent_grid(forall_occupancy<BLOCK, UNROLL, Index, Body, Finalize>(), units, waves);
 }
 
 template <int BLOCK, int UNROLL, class Index, class Body, class Finalize>

@@ -431,11 +431,11 @@ template <class H> int hist_t(H* hist, const int32_t* keys, Index n, int agg, cu
   if (n <= 0) return 0;
   if (agg) {
     using B = HistogramBody<H, true>;
-    const int grid = forall_grid<BLOCK, 8, Index, B, NoFinalize>(n);
+    const int grid = forall_grid<BLOCK, 8, Index, B, NoFinalize>(n, 0, 4);  // atomic-bound: four waves (b200/forall.cuh)
     RB200_CUDA((launch_forall<BLOCK, 8, Index>(st, B{hist, keys}, n, NoFinalize{}, grid)));
   } else {
     using B = HistogramBody<H, false>;
-    const int grid = forall_grid<BLOCK, 8, Index, B, NoFinalize>(n);
+    const int grid = forall_grid<BLOCK, 8, Index, B, NoFinalize>(n, 0, 4);  // atomic-bound: four waves (b200/forall.cuh)
     RB200_CUDA((launch_forall<BLOCK, 8, Index>(st, B{hist, keys}, n, NoFinalize{}, grid)));
   }
   return 0;
@@ -536,11 +536,11 @@ int rb200_atomic_pi(double* pi, int64_t num_bins, int aggregate, rb200_stream_t 
   const double dx = 1.0 / double(num_bins);
   if (aggregate) {
     using B = PiBody<true>;
-    const int grid = forall_grid<BLOCK, 4, Index, B, NoFinalize>((Index)num_bins);
+    const int grid = forall_grid<BLOCK, 4, Index, B, NoFinalize>((Index)num_bins, 0, 4);
     RB200_CUDA((launch_forall<BLOCK, 4, Index>(st, B{pi, dx}, (Index)num_bins, NoFinalize{}, grid)));
   } else {
     using B = PiBody<false>;
-    const int grid = forall_grid<BLOCK, 4, Index, B, NoFinalize>((Index)num_bins);
+    const int grid = forall_grid<BLOCK, 4, Index, B, NoFinalize>((Index)num_bins, 0, 4);
     RB200_CUDA((launch_forall<BLOCK, 4, Index>(st, B{pi, dx}, (Index)num_bins, NoFinalize{}, grid)));
   }
   return 0;
