@@ -182,6 +182,23 @@ for disp in ("Direct", "IndirectFunction"):
     #  Dispatch itself is covered by the functional workgroup suites above.)
 
 
+# ---- launch / reduce-basic: CLASSIC reducer objects captured by a RAJA::launch body and re-captured by RAJA::loop lambdas
+#      (first-level device copies run the grid combine, nested copies fold into their parent); launch / segment
+D = "functional/launch/reduce-basic/"
+for r, dt in (("ReduceSum", "CoreReductionDataTypeList"), ("ReduceMin", "CoreReductionDataTypeList"), ("ReduceBitAnd", "BitwiseReductionDataTypeList")):
+    suite(f"launch-basic-{r}", D + "test-launch-basic-reduce.cpp.in", dict(BACKEND="B200", REDUCETYPE=r, DATATYPES=dt),
+          inject={'#include "RAJA_test-launch-execpol.hpp"': LAUNCH_LISTS})
+for seg in ("ListSegment", "RangeSegment", "RangeStrideSegment"):
+    suite(f"launch-{seg}", "functional/launch/segment/test-launch-segment.cpp.in", dict(BACKEND="B200", SEGTYPES=seg),
+          inject={'#include "RAJA_test-launch-execpol.hpp"': LAUNCH_LISTS})
+
+# ---- kernel / reduce-loc: classic ReduceMinLoc / ReduceMaxLoc (2-D index structs, Views, RAJA::tuple locations) captured by
+#      RAJA::kernel lambdas inside a B200Kernel
+for t in ("Min2D", "Max2D", "Min2DView", "Max2DView", "Min2DViewTuple", "Max2DViewTuple"):
+    suite(f"kernel-reduceloc-{t}", "functional/kernel/reduce-loc/test-kernel-reduceloc.cpp.in", dict(LOC_BACKEND="B200", LOC_TYPE=t),
+          inject={f'#include "test-kernel-reduceloc-{t}.hpp"': KERNEL_LISTS})
+
+
 def generate():
     gen = os.path.join(BUILD, "gen")
     os.makedirs(gen, exist_ok=True)

@@ -28,7 +28,7 @@ def test_refsuite_manifest_and_lists_present():
 @pytest.mark.skipif(not HAVE_REF, reason="reference tree not present")
 def test_refsuite_binaries_were_built():
     names = _suites()
-    assert len(names) >= 50, "run __graft_entry__.build()"
+    assert len(names) >= 100, "run __graft_entry__.build()"
     missing = [n for n in names if not os.path.exists(os.path.join(BUILD, "bin", n))]
     assert not missing, f"not built: {missing}"
 
