@@ -113,7 +113,8 @@ template <class U> struct HistShape {
 
 template <class U>
 __global__ void __launch_bounds__(HistShape<U>::BLOCK, 1)
-histogram_kernel(const U* __restrict__ keys, const long long n, unsigned long long* __restrict__ ghist, const KeyOrder order)
+histogram_kernel(const U* __restrict__ keys, const long long n, unsigned long long* __restrict__ ghist, const KeyOrder order,
+                 unsigned* __restrict__ negzero_flag = nullptr)
 {
   using H = HistShape<U>;
   constexpr int NPASS = H::NPASS, COLS = H::COLS, BLOCK = H::BLOCK, VEC = H::VEC;
@@ -131,12 +132,16 @@ histogram_kernel(const U* __restrict__ keys, const long long n, unsigned long lo
   constexpr U SIGN = U(1) << (BITS - 1);
   U xmask = (order.kind == KEY_SIGNED || order.kind == KEY_FLOAT) ? SIGN : U(0);
   if (order.descending) xmask = ~xmask;
+  bool saw_negzero = false;
   auto run = [&](auto float_c) {
     constexpr bool FLOAT = decltype(float_c)::value;
     auto count = [&](U k) {
       if constexpr (FLOAT) {
         using SU = typename std::make_signed<U>::type;
-        if (k == SIGN) k = 0;
+        if (k == SIGN) {  // -0.0 ranks as +0.0; the sweeps only pay for this special case if it occurs at all
+          k = 0;
+          saw_negzero = true;
+        }
         k ^= (U)((SU)k >> (BITS - 1)) & ~SIGN;
       }
       const U ok = k ^ xmask;
@@ -179,6 +184,7 @@ histogram_kernel(const U* __restrict__ keys, const long long n, unsigned long lo
   };
   if (order.kind == KEY_FLOAT) run(std::true_type{});
   else run(std::false_type{});
+  if (saw_negzero && negzero_flag != nullptr) atomicOr(negzero_flag, 1u);
   __syncthreads();
   for (int b = threadIdx.x; b < NPASS * RADIX; b += BLOCK) {
     uint32_t c = 0;
@@ -191,7 +197,10 @@ histogram_kernel(const U* __restrict__ keys, const long long n, unsigned long lo
 // ---------------------------------------------------------------------------
 // 2. exclusive scan of each pass's 256 bins (one block per pass, 256 threads)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(RADIX) scan_bins_kernel(const unsigned long long* __restrict__ ghist, unsigned long long* __restrict__ bin_base)
+// also: degenerate[p] = 1 when ONE digit value holds all n keys of pass p -- the pass is then the identity permutation and
+// the sweep copies its tiles straight through (low-entropy keys: constant high bytes, small ranges)
+__global__ void __launch_bounds__(RADIX) scan_bins_kernel(const unsigned long long* __restrict__ ghist, unsigned long long* __restrict__ bin_base,
+                                                          const unsigned long long n = 0, unsigned* __restrict__ degenerate = nullptr)
 {
   __shared__ unsigned long long s_w[RADIX / WARP];
   const int d = threadIdx.x, p = blockIdx.x;
@@ -209,6 +218,7 @@ __global__ void __launch_bounds__(RADIX) scan_bins_kernel(const unsigned long lo
   for (int i = 0; i < RADIX / WARP; ++i)
     if (i < (d >> 5)) pre += s_w[i];
   bin_base[p * RADIX + d] = pre + s - c;
+  if (degenerate != nullptr && n > 0 && c == n) degenerate[p] = 1u;
 }
 
 // ---------------------------------------------------------------------------
@@ -587,17 +597,55 @@ onesweep_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 template <class U, bool FLOAT> struct RadixDigit {
   static constexpr bool PEER_OUT = false;
   static constexpr int BUCKETS = RADIX;
+  static constexpr bool ENCODE_ON_LOAD = false, DECODE_ON_STORE = false;
   int shift;
   unsigned dxor;
+  const unsigned* degenerate = nullptr;  // device flag of this pass: all keys share one digit value (scan_bins_kernel)
+  B200_D void prepare() {}
+  B200_D bool identity_pass() const { return degenerate != nullptr && *degenerate != 0u; }
   B200_D unsigned operator()(U k) const { return sweep_digit<FLOAT>(k, shift, dxor); }
+};
+
+// Floating-point keys travel BETWEEN the passes of one sort in the order-preserving encoding (sign flipped for positives,
+// all bits flipped for negatives): the first pass encodes on load, the last decodes on store, and in between a digit is a
+// shift and a mask -- the sign-dependent transform used to be evaluated three times per key and pass, and the 64-bit sweep is
+// ALU-bound (ALU pipe 75 %, profiles/r02_onesweep_f64_ncu.txt).  -0.0 must rank as +0.0 (they compare equal, a stable sort
+// keeps their input order) while the stored key keeps its sign: its code (SIGN - 1) is read as +0.0's (SIGN) when a digit is
+// taken -- but only if the histogram kernel, which sees every key first, found a -0.0 at all (one device flag; otherwise the
+// compare is skipped).
+enum FloatPass : int { FLOAT_FIRST = 1, FLOAT_MIDDLE = 2, FLOAT_LAST = 3 };
+template <class U, int PASS> struct FloatDigit {
+  static constexpr bool PEER_OUT = false;
+  static constexpr int BUCKETS = RADIX;
+  static constexpr bool ENCODE_ON_LOAD = (PASS == FLOAT_FIRST), DECODE_ON_STORE = (PASS == FLOAT_LAST);
+  static constexpr int BITS = 8 * sizeof(U);
+  static constexpr U SIGN = U(1) << (BITS - 1);
+  using SU = typename std::make_signed<U>::type;
+  int shift;
+  unsigned dxor;                  // 0xff for descending order
+  const unsigned* negzero_flag;   // device: non-zero if the keys contain a -0.0
+  const unsigned* degenerate;     // device flag of this pass: all keys share one digit value
+  bool negzero;
+  B200_D void prepare() { negzero = (*negzero_flag != 0u); }
+  B200_D bool identity_pass() const { return degenerate != nullptr && *degenerate != 0u; }
+  B200_D static U encode(U k) { return k ^ ((U)((SU)k >> (BITS - 1)) | SIGN); }
+  B200_D static U decode(U o) { return o ^ ((U)(~(SU)o >> (BITS - 1)) | SIGN); }
+  B200_D unsigned operator()(U o) const
+  {
+    if (negzero && o == U(SIGN - 1)) o = SIGN;
+    return ((unsigned)(o >> shift) & (RADIX - 1)) ^ dxor;
+  }
 };
 constexpr int MAX_SPLITTERS = 7;
 template <class U> struct SplitDigit {
   static constexpr bool PEER_OUT = false;
   static constexpr int BUCKETS = 8;  // MAX_SPLITTERS + 1: few, long runs per tile -> line-aligned write-out
+  static constexpr bool ENCODE_ON_LOAD = false, DECODE_ON_STORE = false;
   U s[MAX_SPLITTERS];  // already mapped with to_ordered(), non-decreasing
   int nsplit;
   KeyOrder order;
+  B200_D void prepare() {}
+  B200_D bool identity_pass() const { return false; }
   B200_D U splitter(int i) const { return s[i]; }
   B200_D unsigned operator()(U k) const
   {
@@ -664,6 +712,7 @@ template <class U, class VT, class C, class S> struct LateSmem {
   G gbase[RADIX];           // global position of tile-rank r of digit d = gbase[d] + r (mod 2^bits)
   uint32_t wtot[RADIX / WARP];
   long long tile;
+  int identity;  // this pass is an identity permutation (all keys share one digit value)
 #ifdef RB200_LB_TRACE
   unsigned long long t_compute, t_lb;  // arrival times at the barrier before the write-out
 #endif
@@ -679,8 +728,10 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
                      const unsigned long long* __restrict__ bin_base,  // [256] of this pass
                      C* lookback,                                      // [ngroups][256] group words, then [ntiles][256] u16 tile counts; zero on entry
                      unsigned* ticket,                                 // zero on entry
-                     const DigitFn digit)
+                     const DigitFn digit_in)
 {
+  DigitFn digit = digit_in;
+  digit.prepare();
   using SM = LateSmem<U, VT, C, S>;
   using F = LookbackFlags<C>;
   using G = typename SM::G;
@@ -694,7 +745,12 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
 
   const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
   const bool compute = tid < BLOCK;
-  if (tid == 0) s.tile = (long long)atomicAdd(ticket, 1u);
+  if (tid == 0) {
+    // the flag load travels together with the ticket atomic: no extra round trip in front of the key loads
+    const bool ident = digit.identity_pass();
+    s.tile = (long long)atomicAdd(ticket, 1u);
+    s.identity = ident ? 1 : 0;
+  }
 #ifdef RB200_LB_TRACE
   if (tid == 0) {
     s.t_compute = 0;
@@ -707,6 +763,19 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
   const long long tile_base = tile * TILE;
   const int tile_count = (int)((n - tile_base) < (long long)TILE ? (n - tile_base) : (long long)TILE);
   const bool full = (tile_count == TILE);
+  if (s.identity) {
+    // every key of this pass has the same digit: the stable permutation is the identity.  Copy the tile straight through
+    // (no ranking, no look-back: every tile's destination is its own position), encoding / decoding floating-point keys
+    // exactly as the general path would.
+    for (int i = tid; i < tile_count; i += S::THREADS) {
+      U k = ld_stream(keys_in + tile_base + i);
+      if constexpr (DigitFn::ENCODE_ON_LOAD) k = DigitFn::encode(k);
+      if constexpr (DigitFn::DECODE_ON_STORE) k = DigitFn::decode(k);
+      keys_out[tile_base + i] = k;
+      if constexpr (HAS_VALUES) vals_out[tile_base + i] = ld_stream(vals_in + tile_base + i);
+    }
+    return;
+  }
   const int wofs = w * (WARP * ITEMS);  // this warp's first item within the tile
   // Look-back words.  A tile publishes its digit counts as 16-bit words (count + 1; 0 = not yet) in
   // local16 right after the ranking, and its inclusive prefixes (value | GLOBAL) in `lookback` once
@@ -730,6 +799,10 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
         const int i = wofs + j * WARP + l;
         key[j] = (i < tile_count) ? ld_stream(keys_in + tile_base + i) : U(0);
       }
+    }
+    if constexpr (DigitFn::ENCODE_ON_LOAD) {
+#pragma unroll
+      for (int j = 0; j < ITEMS; ++j) key[j] = DigitFn::encode(key[j]);
     }
   } else if (tid == BLOCK) {
     if constexpr (HAS_VALUES) prefetch_l2(vals_in + tile_base, vals_in + tile_base + tile_count);
@@ -1053,17 +1126,20 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
             const uint2 kv = pairs[i];
             const unsigned d = digit((U)kv.x);
             const G dst = s.gbase[d] + (G)i;
+            U kx = (U)kv.x;
+            if constexpr (DigitFn::DECODE_ON_STORE) kx = DigitFn::decode(kx);
             if constexpr (DigitFn::PEER_OUT) {
-              digit.kdst[d][dst] = (U)kv.x;
+              digit.kdst[d][dst] = kx;
               digit.vdst[d][dst] = bit_cast_<VT>(kv.y);
             } else {
-              keys_out[dst] = (U)kv.x;
+              keys_out[dst] = kx;
               vals_out[dst] = bit_cast_<VT>(kv.y);
             }
           } else {
-            const U k = s.keys[i];
+            U k = s.keys[i];
             const unsigned d = digit(k);
             const G dst = s.gbase[d] + (G)i;
+            if constexpr (DigitFn::DECODE_ON_STORE) k = DigitFn::decode(k);
             if constexpr (DigitFn::PEER_OUT) {
               digit.kdst[d][dst] = k;
               if constexpr (HAS_VALUES) digit.vdst[d][dst] = s.vals[i];
@@ -1112,7 +1188,7 @@ template <class U, class VT, class S = typename Tuning<U, VT>::shape> inline lon
 template <class U, class VT, class S = typename Tuning<U, VT>::shape> inline size_t workspace_bytes(long long n)
 {
   constexpr int NPASS = sizeof(U);
-  size_t header = (size_t)NPASS * RADIX * 8 * 2 + 256;
+  size_t header = (size_t)NPASS * RADIX * 8 * 2 + 512;
   size_t cbytes = (n < (1ll << 30)) ? 4 : 8;
   return header + NPASS * lookback_bytes<S>(num_tiles<U, VT, S>(n), cbytes);
 }
@@ -1143,28 +1219,60 @@ template <class U, class VT, bool FLOAT, class C, class S> struct SweepKernel {
 
 template <class U, class VT, bool FLOAT, class C, class S>
 inline cudaError_t launch_pass_k(cudaStream_t stream, const U* kin, U* kout, const VT* vin, VT* vout, long long n,
-                                 const unsigned long long* bin_base, void* lookback, unsigned* ticket, int shift, unsigned dxor, long long ntiles)
+                                 const unsigned long long* bin_base, void* lookback, unsigned* ticket, int shift, unsigned dxor, long long ntiles,
+                                 const unsigned* degenerate = nullptr)
 {
   using K = SweepKernel<U, VT, FLOAT, C, S>;
   constexpr auto kern = K::kernel();
   cudaError_t e = configure_once<kern>((int)sizeof(typename K::SM));
   if (e != cudaSuccess) return e;
   if constexpr (S::MATCH >= 3)
-    kern<<<(unsigned)ntiles, S::THREADS, sizeof(typename K::SM), stream>>>(kin, kout, vin, vout, n, bin_base, (C*)lookback, ticket, RadixDigit<U, FLOAT>{shift, dxor});
+    kern<<<(unsigned)ntiles, S::THREADS, sizeof(typename K::SM), stream>>>(kin, kout, vin, vout, n, bin_base, (C*)lookback, ticket, RadixDigit<U, FLOAT>{shift, dxor, degenerate});
   else
     kern<<<(unsigned)ntiles, S::THREADS, sizeof(typename K::SM), stream>>>(kin, kout, vin, vout, n, bin_base, (C*)lookback, ticket, shift, dxor);
   return cudaGetLastError();
 }
 
+// one pass of a floating-point sort with the keys in the ordered encoding between the passes (late-count kernel only)
+template <class U, class VT, int PASS, class C, class S>
+inline cudaError_t launch_pass_float(cudaStream_t stream, const U* kin, U* kout, const VT* vin, VT* vout, long long n, const unsigned long long* bin_base,
+                                     void* lookback, unsigned* ticket, int shift, bool descending, const unsigned* negzero_flag, long long ntiles,
+                                     const unsigned* degenerate = nullptr)
+{
+  using D = FloatDigit<U, PASS>;
+  constexpr auto kern = &onesweep_late_kernel<U, VT, D, C, S>;
+  cudaError_t e = configure_once<kern>((int)sizeof(LateSmem<U, VT, C, S>));
+  if (e != cudaSuccess) return e;
+  D digit;
+  digit.shift = shift;
+  digit.dxor = descending ? (unsigned)(RADIX - 1) : 0u;
+  digit.negzero_flag = negzero_flag;
+  digit.degenerate = degenerate;
+  digit.negzero = false;
+  kern<<<(unsigned)ntiles, S::THREADS, sizeof(LateSmem<U, VT, C, S>), stream>>>(kin, kout, vin, vout, n, bin_base, (C*)lookback, ticket, digit);
+  return cudaGetLastError();
+}
+
+// pass_pos: 0 = first, 1 = middle, 2 = last pass of the sort; negzero_flag: device word the histogram kernel sets when the
+// keys contain a -0.0 (floating-point keys only)
 template <class U, class VT, class C, class S>
 inline cudaError_t launch_pass(cudaStream_t stream, const U* kin, U* kout, const VT* vin, VT* vout, long long n,
-                               const unsigned long long* bin_base, void* lookback, unsigned* ticket, int shift, KeyOrder order)
+                               const unsigned long long* bin_base, void* lookback, unsigned* ticket, int shift, KeyOrder order, int pass_pos = 1,
+                               const unsigned* negzero_flag = nullptr, const unsigned* degenerate = nullptr)
 {
   const long long ntiles = num_tiles<U, VT, S>(n);
   const unsigned dxor = digit_xor<U>(order, shift);
   LaunchScope scope("onesweep_kernel", stream);
-  if (order.kind == KEY_FLOAT) return launch_pass_k<U, VT, true, C, S>(stream, kin, kout, vin, vout, n, bin_base, lookback, ticket, shift, dxor, ntiles);
-  return launch_pass_k<U, VT, false, C, S>(stream, kin, kout, vin, vout, n, bin_base, lookback, ticket, shift, dxor, ntiles);
+  if constexpr (S::MATCH >= 3) {
+    if (order.kind == KEY_FLOAT && negzero_flag != nullptr) {
+      const bool desc = order.descending != 0;
+      if (pass_pos == 0) return launch_pass_float<U, VT, FLOAT_FIRST, C, S>(stream, kin, kout, vin, vout, n, bin_base, lookback, ticket, shift, desc, negzero_flag, ntiles, degenerate);
+      if (pass_pos == 2) return launch_pass_float<U, VT, FLOAT_LAST, C, S>(stream, kin, kout, vin, vout, n, bin_base, lookback, ticket, shift, desc, negzero_flag, ntiles, degenerate);
+      return launch_pass_float<U, VT, FLOAT_MIDDLE, C, S>(stream, kin, kout, vin, vout, n, bin_base, lookback, ticket, shift, desc, negzero_flag, ntiles, degenerate);
+    }
+  }
+  if (order.kind == KEY_FLOAT) return launch_pass_k<U, VT, true, C, S>(stream, kin, kout, vin, vout, n, bin_base, lookback, ticket, shift, dxor, ntiles, degenerate);
+  return launch_pass_k<U, VT, false, C, S>(stream, kin, kout, vin, vout, n, bin_base, lookback, ticket, shift, dxor, ntiles, degenerate);
 }
 
 // Sorts n keys (and values) held in (keys, vals) using (keys_alt, vals_alt) as the
@@ -1175,12 +1283,14 @@ inline cudaError_t sort(cudaStream_t stream, U* keys, U* keys_alt, VT* vals, VT*
   if (n <= 1) return cudaSuccess;
   constexpr int NPASS = sizeof(U);
   static_assert(NPASS % 2 == 0, "even pass count keeps the result in the caller's buffer");
-  const size_t header = (size_t)NPASS * RADIX * 8 * 2 + 256;
+  const size_t header = (size_t)NPASS * RADIX * 8 * 2 + 512;
   unsigned long long* ghist = (unsigned long long*)workspace;
   unsigned long long* bin_base = ghist + NPASS * RADIX;
   unsigned* tickets = (unsigned*)(bin_base + NPASS * RADIX);
   const bool small = n < (1ll << 30);
   const size_t lb_bytes = lookback_bytes<S>(num_tiles<U, VT, S>(n), small ? 4 : 8);
+  unsigned* const degenerate_flags = tickets + 64;  // [NPASS]: the pass is an identity permutation (scan_bins_kernel); inside the 512-byte ticket area
+  unsigned* const negzero_flag = tickets + 72;      // the keys contain a -0.0 (histogram_kernel)
 
   cudaError_t e = cudaMemsetAsync(workspace, 0, header + NPASS * lb_bytes, stream);
   if (e != cudaSuccess) return e;
@@ -1192,11 +1302,11 @@ inline cudaError_t sort(cudaStream_t stream, U* keys, U* keys_alt, VT* vals, VT*
     if (grid > device_info().sm_count) grid = device_info().sm_count;
     {
       LaunchScope scope("histogram_kernel", stream);
-      histogram_kernel<U><<<(unsigned)grid, H::BLOCK, H::SMEM, stream>>>(keys, n, ghist, order);
+      histogram_kernel<U><<<(unsigned)grid, H::BLOCK, H::SMEM, stream>>>(keys, n, ghist, order, negzero_flag);
     }
     {
       LaunchScope scope("scan_bins_kernel", stream);
-      scan_bins_kernel<<<NPASS, RADIX, 0, stream>>>(ghist, bin_base);
+      scan_bins_kernel<<<NPASS, RADIX, 0, stream>>>(ghist, bin_base, (unsigned long long)n, degenerate_flags);
     }
   }
   for (int p = 0; p < NPASS; ++p) {
@@ -1205,10 +1315,12 @@ inline cudaError_t sort(cudaStream_t stream, U* keys, U* keys_alt, VT* vals, VT*
     const VT* vin = (p & 1) ? vals_alt : vals;
     VT* vout = (p & 1) ? vals : vals_alt;
     void* lookback = (char*)workspace + header + p * lb_bytes;
+    const int pos = p == 0 ? 0 : (p == NPASS - 1 ? 2 : 1);
     if (small)
-      e = launch_pass<U, VT, uint32_t, S>(stream, kin, kout, vin, vout, n, bin_base + p * RADIX, lookback, tickets + p, p * RADIX_BITS, order);
+      e = launch_pass<U, VT, uint32_t, S>(stream, kin, kout, vin, vout, n, bin_base + p * RADIX, lookback, tickets + p, p * RADIX_BITS, order, pos, negzero_flag, degenerate_flags + p);
     else
-      e = launch_pass<U, VT, unsigned long long, S>(stream, kin, kout, vin, vout, n, bin_base + p * RADIX, lookback, tickets + p, p * RADIX_BITS, order);
+      e = launch_pass<U, VT, unsigned long long, S>(stream, kin, kout, vin, vout, n, bin_base + p * RADIX, lookback, tickets + p, p * RADIX_BITS, order, pos,
+                                                    negzero_flag, degenerate_flags + p);
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
@@ -1307,7 +1419,7 @@ template <class U, class VT, class S = typename PartitionTuning<U, VT>::shape, c
 inline cudaError_t bucket_counts(cudaStream_t stream, const U* keys_in, long long n, const DigitFn& digit, unsigned long long* counts_dev, void* workspace)
 {
   constexpr int NPASS = sizeof(U);
-  const size_t header = (size_t)NPASS * RADIX * 8 * 2 + 256;
+  const size_t header = (size_t)NPASS * RADIX * 8 * 2 + 512;
   unsigned long long* ghist = (unsigned long long*)workspace;
   const bool small = n < (1ll << 30);
   const long long ntiles = num_tiles<U, VT, S>(n > 0 ? n : 1);
@@ -1336,7 +1448,7 @@ inline cudaError_t split_sweep(cudaStream_t stream, const U* keys_in, U* keys_ou
 {
   if (n <= 0) return cudaSuccess;
   constexpr int NPASS = sizeof(U);
-  const size_t header = (size_t)NPASS * RADIX * 8 * 2 + 256;
+  const size_t header = (size_t)NPASS * RADIX * 8 * 2 + 512;
   unsigned long long* ghist = (unsigned long long*)workspace;
   unsigned long long* bin_base = ghist + NPASS * RADIX;
   unsigned* tickets = (unsigned*)(bin_base + NPASS * RADIX);

@@ -16,6 +16,9 @@ __constant__ unsigned long long c_splitters[CONST_SPLIT_SLOTS][MAX_SPLITTERS + 1
 template <class U> struct ConstSplitDigit {
   static constexpr bool PEER_OUT = false;
   static constexpr int BUCKETS = 8;
+  static constexpr bool ENCODE_ON_LOAD = false, DECODE_ON_STORE = false;
+  B200_D void prepare() {}
+  B200_D bool identity_pass() const { return false; }
   int slot;
   int nsplit;
   KeyOrder order;

@@ -295,6 +295,35 @@ def test_sort_float_special_values(rb, orc, dtype):
         assert np.array_equal(host(k).view(np.uint8), ok.view(np.uint8))  # stored keys keep their sign bit
 
 
+@pytest.mark.parametrize("dtype", [np.uint32, np.int32, np.uint64, np.int64, np.float32, np.float64])
+def test_sort_degenerate_digit_passes(rb, orc, dtype):
+    """keys whose digits are constant in several passes (constant high bytes, constant low bytes, all keys equal): those passes are
+    identity permutations and take the copy-through path of the sweep (radix_sort.cuh: identity_pass); floating-point keys are
+    encoded / decoded on the way through exactly as in the general path"""
+    rng = np.random.default_rng(23)
+    n = 70_001
+    if np.issubdtype(dtype, np.floating):
+        cases = [(1.0 + rng.integers(0, 200, n) / 256.0).astype(dtype),            # only a few mantissa bits vary
+                 (-(3.0 + rng.integers(0, 5, n))).astype(dtype),                   # negative, tiny alphabet
+                 np.full(n, -0.0, dtype=dtype), np.where(rng.integers(0, 2, n) == 0, 0.0, -0.0).astype(dtype)]
+    else:
+        info = np.iinfo(dtype)
+        cases = [(rng.integers(0, 200, n)).astype(dtype),                           # constant high bytes
+                 ((rng.integers(0, 200, n).astype(np.uint64) << np.uint64(8 * (np.dtype(dtype).itemsize - 1) - 1))).astype(dtype),  # constant low bytes
+                 np.full(n, info.max // 3, dtype=dtype)]                            # every pass degenerate
+    vals = np.arange(n, dtype=np.uint32)
+    for keys in cases:
+        for desc in (False, True):
+            k, v = dev(keys), dev(vals)
+            rb.stable_sort_pairs(k, v, rb.operators.greater if desc else rb.operators.less)
+            ok, ov = orc.stable_sort_pairs(keys, vals, desc)
+            assert np.array_equal(host(v), ov)
+            assert np.array_equal(host(k).view(np.uint8), ok.view(np.uint8))
+            k2 = dev(keys)
+            rb.stable_sort(k2, rb.operators.greater if desc else rb.operators.less)
+            assert np.array_equal(host(k2).view(np.uint8), orc.stable_sort(keys, desc).view(np.uint8))
+
+
 def test_sort_trivial_sizes_and_buffered_variant(rb, orc):
     for n in (0, 1):
         k = torch.arange(n, dtype=torch.int32, device="cuda")

@@ -27,6 +27,14 @@ for what in "$@"; do
               for t in forall-basic-ReduceSum scan-Inclusive kernel-basic-param; do
                 echo "== racecheck $t"; timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 tests/refsuite/_build/bin/$t --gtest_brief=1 2>&1 | tail -4; done > $OUT/sanitizer_racecheck.txt 2>&1
               echo "sanitize done"; grep -c "ERROR SUMMARY: 0 errors" $OUT/sanitizer_memcheck.txt $OUT/sanitizer_racecheck.txt ;;
+    ncu-full) B="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-verify --no-reference-gpu"
+              timeout 900 ncu --set full --clock-control none --import-source on -k regex:onesweep_late_kernel -s 9 -c 1 -f -o $OUT/ncu_onesweep_u32 $B > $OUT/ncu_onesweep.log 2>&1; echo "ncu onesweep rc=$?"
+              timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 6 -c 1 -f -o $OUT/ncu_scan_i32 $B > $OUT/ncu_scan.log 2>&1; echo "ncu scan rc=$?"
+              timeout 900 ncu --set full --clock-control none --import-source on -k regex:forall_kernel -s 6 -c 1 -f -o $OUT/ncu_forall_dot $B > $OUT/ncu_forall.log 2>&1; echo "ncu forall rc=$?"
+              timeout 900 ncu --set full --clock-control none --import-source on -k regex:onesweep_late_kernel -s 2 -c 1 -f -o $OUT/ncu_onesweep_f64 python tools/run_path.py --path sortf64 --reps 1 > $OUT/ncu_onesweep_f64.log 2>&1; echo "ncu onesweep f64 rc=$?"
+              # the reports themselves (tens of MB each with sources) do not fit the 64 MiB that travels back: keep the text pages
+              for r in $OUT/*.ncu-rep; do b=${r%.ncu-rep}; ncu -i $r --page details > ${b}_details.txt 2>&1; ncu -i $r --page raw --csv > ${b}_raw.csv 2>&1; rm -f $r; done
+              du -sh $OUT ;;
     paths)    timeout 900 python tools/run_path.py > $OUT/paths.txt 2>&1; echo "paths rc=$?" ;;
     *)        echo "running: $what"; timeout 1800 bash -c "$what" > $OUT/cmd_$(date +%s).txt 2>&1; echo "rc=$?" ;;
   esac
