@@ -155,11 +155,12 @@ forall_impl(resources::Cuda res, b200_exec_explicit<BLOCK_SIZE, GRID_SIZE, Async
   {
     cudaStream_t stream = res.get_stream();
     // b200_exec_grid<BLOCK, GRID>: the caller's grid (never more blocks than units of work); otherwise SMs x resident CTAs
-    // User lambdas are opaque.  Without reducers: four waves of CTAs, which lets the block scheduler balance bodies of uneven
-    // cost (atomics: -9 %) and is free for streaming ones (b200/forall.cuh: persistent_grid).  With reducers -- parameters of
+    // User lambdas are opaque.  Without reducers: 32 waves of CTAs (256 CTAs per SM at BLOCK 256), which lets the block scheduler
+    // balance bodies of uneven cost (atomics: -12 %, level with one block per 256 indices) and is free for streaming ones
+    // (b200/forall.cuh: persistent_grid).  With reducers -- parameters of
     // the pack, or classic / multi reducer objects that announce themselves while the body is copied below -- one wave: every
     // CTA pays the block + grid combine (and a multi-reducer its flush), so fewer CTAs are cheaper.
-    constexpr int waves = empty ? 4 : 1;
+    constexpr int waves = empty ? 32 : 1;
     int grid = ::b200::forall_grid<(int)BLOCK_SIZE, UNROLL, IndexType, BodyT, FinT>(len, (long long)GRID_SIZE, waves);
     LaunchInfo info {grid, (int)BLOCK_SIZE, stream, res};
     if constexpr (!empty) RAJA::expt::ParamMultiplexer::parampack_init(pol, f_params, info);

@@ -89,9 +89,9 @@ forall_kernel(const __grid_constant__ Body body_in, const Index len, const __gri
 // more blocks than tiles.
 // `waves` > 1 oversubscribes the device: the hardware block scheduler then hands a fresh CTA to whichever SM frees a slot,
 // which balances loop bodies whose cost is uneven or contended (atomics: a histogram of 2^28 keys into 64 K bins runs at
-// 1.93 ms with one wave at any UNROLL and any number of resident CTAs, 1.77 ms with four waves, 1.70 ms with the reference's one
-// block per 256 indices) and costs streaming bodies nothing (triad 6.60-6.63 TB/s from 1 to 8 waves):
-// profiles/r02_forall_grid_sweep.txt.
+// 1.93 ms with one wave at any UNROLL and any number of resident CTAs, 1.77 ms with four waves, 1.708 ms with 32 waves
+// (256 CTAs per SM), 1.703 ms with the reference's one block per 256 indices) and costs streaming bodies nothing (triad
+// 6.60-6.63 TB/s from 1 to 8 waves): profiles/r02_forall_grid_sweep.txt.
 inline int persistent_grid(int occ_per_sm, long long tiles, int waves = 1)
 {
   long long g = (long long)device_info().sm_count * (occ_per_sm > 0 ? occ_per_sm : 1) * (waves > 0 ? waves : 1);

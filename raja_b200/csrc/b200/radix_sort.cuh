@@ -601,7 +601,6 @@ template <class U, bool FLOAT> struct RadixDigit {
   int shift;
   unsigned dxor;
   const unsigned* degenerate = nullptr;  // device flag of this pass: all keys share one digit value (scan_bins_kernel)
-  B200_D void prepare() {}
   B200_D bool identity_pass() const { return degenerate != nullptr && *degenerate != 0u; }
   B200_D unsigned operator()(U k) const { return sweep_digit<FLOAT>(k, shift, dxor); }
 };
@@ -614,28 +613,36 @@ template <class U, bool FLOAT> struct RadixDigit {
 // taken -- but only if the histogram kernel, which sees every key first, found a -0.0 at all (one device flag; otherwise the
 // compare is skipped).
 enum FloatPass : int { FLOAT_FIRST = 1, FLOAT_MIDDLE = 2, FLOAT_LAST = 3 };
-template <class U, int PASS> struct FloatDigit {
+// NEGZERO = false is the functor the host passes; the kernel reads the flag once and runs the body instantiated for
+// NEGZERO = true (its Twin) only when the keys do contain a -0.0 -- the compare + selects of that case cost 13 % of an
+// ALU-bound 64-bit sweep when they were evaluated behind a run-time flag (3 digit evaluations per key and pass).
+template <class U, int PASS, bool NEGZERO = false> struct FloatDigit {
   static constexpr bool PEER_OUT = false;
   static constexpr int BUCKETS = RADIX;
   static constexpr bool ENCODE_ON_LOAD = (PASS == FLOAT_FIRST), DECODE_ON_STORE = (PASS == FLOAT_LAST);
   static constexpr int BITS = 8 * sizeof(U);
   static constexpr U SIGN = U(1) << (BITS - 1);
   using SU = typename std::make_signed<U>::type;
+  using Twin = FloatDigit<U, PASS, true>;
   int shift;
   unsigned dxor;                  // 0xff for descending order
   const unsigned* negzero_flag;   // device: non-zero if the keys contain a -0.0
   const unsigned* degenerate;     // device flag of this pass: all keys share one digit value
-  bool negzero;
-  B200_D void prepare() { negzero = (*negzero_flag != 0u); }
+  B200_D bool use_twin() const { return !NEGZERO && *negzero_flag != 0u; }
+  B200_D Twin twin() const { return Twin{shift, dxor, negzero_flag, degenerate}; }
   B200_D bool identity_pass() const { return degenerate != nullptr && *degenerate != 0u; }
   B200_D static U encode(U k) { return k ^ ((U)((SU)k >> (BITS - 1)) | SIGN); }
   B200_D static U decode(U o) { return o ^ ((U)(~(SU)o >> (BITS - 1)) | SIGN); }
   B200_D unsigned operator()(U o) const
   {
-    if (negzero && o == U(SIGN - 1)) o = SIGN;
+    if constexpr (NEGZERO) {
+      if (o == U(SIGN - 1)) o = SIGN;
+    }
     return ((unsigned)(o >> shift) & (RADIX - 1)) ^ dxor;
   }
 };
+template <class D, class = void> struct HasTwin : std::false_type {};
+template <class D> struct HasTwin<D, std::void_t<typename D::Twin>> : std::true_type {};
 constexpr int MAX_SPLITTERS = 7;
 template <class U> struct SplitDigit {
   static constexpr bool PEER_OUT = false;
@@ -644,7 +651,6 @@ template <class U> struct SplitDigit {
   U s[MAX_SPLITTERS];  // already mapped with to_ordered(), non-decreasing
   int nsplit;
   KeyOrder order;
-  B200_D void prepare() {}
   B200_D bool identity_pass() const { return false; }
   B200_D U splitter(int i) const { return s[i]; }
   B200_D unsigned operator()(U k) const
@@ -721,17 +727,14 @@ template <class U, class VT, class C, class S> struct LateSmem {
 };
 
 template <class U, class VT, class DigitFn, class C, class S>
-__global__ void __launch_bounds__(S::THREADS, S::MIN_CTAS)
-onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
-                     const VT* __restrict__ vals_in, VT* __restrict__ vals_out,
-                     const long long n,
-                     const unsigned long long* __restrict__ bin_base,  // [256] of this pass
-                     C* lookback,                                      // [ngroups][256] group words, then [ntiles][256] u16 tile counts; zero on entry
-                     unsigned* ticket,                                 // zero on entry
-                     const DigitFn digit_in)
+B200_D void onesweep_late_body(const U* __restrict__ keys_in, U* __restrict__ keys_out,
+                               const VT* __restrict__ vals_in, VT* __restrict__ vals_out,
+                               const long long n,
+                               const unsigned long long* __restrict__ bin_base,  // [256] of this pass
+                               C* lookback,                                      // [ngroups][256] group words, then [ntiles][256] u16 tile counts; zero on entry
+                               unsigned* ticket,                                 // zero on entry
+                               const DigitFn& digit)
 {
-  DigitFn digit = digit_in;
-  digit.prepare();
   using SM = LateSmem<U, VT, C, S>;
   using F = LookbackFlags<C>;
   using G = typename SM::G;
@@ -1156,6 +1159,22 @@ onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out,
   }
 }
 
+template <class U, class VT, class DigitFn, class C, class S>
+__global__ void __launch_bounds__(S::THREADS, S::MIN_CTAS)
+onesweep_late_kernel(const U* __restrict__ keys_in, U* __restrict__ keys_out, const VT* __restrict__ vals_in, VT* __restrict__ vals_out, const long long n,
+                     const unsigned long long* __restrict__ bin_base, C* lookback, unsigned* ticket, const DigitFn digit)
+{
+  if constexpr (HasTwin<DigitFn>::value) {
+    // the rare variant of the digit functor (keys contain a -0.0): same body, instantiated a second time; the branch is
+    // uniform over the grid
+    if (digit.use_twin()) {
+      onesweep_late_body<U, VT, typename DigitFn::Twin, C, S>(keys_in, keys_out, vals_in, vals_out, n, bin_base, lookback, ticket, digit.twin());
+      return;
+    }
+  }
+  onesweep_late_body<U, VT, DigitFn, C, S>(keys_in, keys_out, vals_in, vals_out, n, bin_base, lookback, ticket, digit);
+}
+
 // ---------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------
@@ -1248,7 +1267,6 @@ inline cudaError_t launch_pass_float(cudaStream_t stream, const U* kin, U* kout,
   digit.dxor = descending ? (unsigned)(RADIX - 1) : 0u;
   digit.negzero_flag = negzero_flag;
   digit.degenerate = degenerate;
-  digit.negzero = false;
   kern<<<(unsigned)ntiles, S::THREADS, sizeof(LateSmem<U, VT, C, S>), stream>>>(kin, kout, vin, vout, n, bin_base, (C*)lookback, ticket, digit);
   return cudaGetLastError();
 }

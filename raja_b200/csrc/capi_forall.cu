@@ -431,11 +431,11 @@ template <class H> int hist_t(H* hist, const int32_t* keys, Index n, int agg, cu
   if (n <= 0) return 0;
   if (agg) {
     using B = HistogramBody<H, true>;
-    const int grid = forall_grid<BLOCK, 8, Index, B, NoFinalize>(n, 0, 4);  // atomic-bound: four waves (b200/forall.cuh)
+    const int grid = forall_grid<BLOCK, 8, Index, B, NoFinalize>(n, 0, 32);  // atomic-bound: 32 waves (b200/forall.cuh)
     RB200_CUDA((launch_forall<BLOCK, 8, Index>(st, B{hist, keys}, n, NoFinalize{}, grid)));
   } else {
     using B = HistogramBody<H, false>;
-    const int grid = forall_grid<BLOCK, 8, Index, B, NoFinalize>(n, 0, 4);  // atomic-bound: four waves (b200/forall.cuh)
+    const int grid = forall_grid<BLOCK, 8, Index, B, NoFinalize>(n, 0, 32);  // atomic-bound: 32 waves (b200/forall.cuh)
     RB200_CUDA((launch_forall<BLOCK, 8, Index>(st, B{hist, keys}, n, NoFinalize{}, grid)));
   }
   return 0;

@@ -17,7 +17,6 @@ template <class U> struct ConstSplitDigit {
   static constexpr bool PEER_OUT = false;
   static constexpr int BUCKETS = 8;
   static constexpr bool ENCODE_ON_LOAD = false, DECODE_ON_STORE = false;
-  B200_D void prepare() {}
   B200_D bool identity_pass() const { return false; }
   int slot;
   int nsplit;

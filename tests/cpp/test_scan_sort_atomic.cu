@@ -57,7 +57,45 @@ template <class T, class Op> void test_scan(long N, bool exact)
   cudaFree(din); cudaFree(dout);
 }
 
-template <class K> void test_sort(long N)
+// an element type the TMA scan is not written for: 16 bytes, with a functor that is associative but NOT commutative
+// (composition of the affine maps x -> a x + b over the integers mod 2^64)
+struct Affine { unsigned long a, b; bool operator==(const Affine& o) const { return a == o.a && b == o.b; } };
+struct Compose { RAJA_HOST_DEVICE Affine operator()(const Affine& f, const Affine& g) const { return Affine {f.a * g.a, f.b * g.a + g.b}; } };
+void test_scan_struct(long N)
+{
+  std::vector<Affine> in(N), ref(N);
+  std::mt19937 gen(11 + (unsigned)N);
+  for (auto& f : in) f = Affine {(unsigned long)(gen() | 1u), (unsigned long)gen()};
+  Affine* din = to_dev(in);
+  Affine* dout; cudaMalloc(&dout, N * sizeof(Affine) + 16);
+  const Affine seed {3, 7};
+  RAJA::inclusive_scan<RAJA::seq_exec>(RAJA::make_span(in.data(), N), RAJA::make_span(ref.data(), N), Compose {});
+  RAJA::inclusive_scan<EXEC>(RAJA::make_span(din, N), RAJA::make_span(dout, N), Compose {});
+  EXPECT(to_host(dout, N) == ref);
+  RAJA::exclusive_scan<RAJA::seq_exec>(RAJA::make_span(in.data(), N), RAJA::make_span(ref.data(), N), Compose {}, seed);
+  RAJA::exclusive_scan<EXEC>(RAJA::make_span(din, N), RAJA::make_span(dout, N), Compose {}, seed);
+  EXPECT(to_host(dout, N) == ref);
+  std::vector<Affine> tmp = in;
+  RAJA::inclusive_scan_inplace<RAJA::seq_exec>(RAJA::make_span(tmp.data(), N), Compose {});
+  RAJA::inclusive_scan_inplace<EXEC>(RAJA::make_span(din, N), Compose {});
+  EXPECT(to_host(din, N) == tmp);
+  tmp = in;
+  cudaMemcpy(din, in.data(), N * sizeof(Affine), cudaMemcpyHostToDevice);
+  RAJA::exclusive_scan_inplace<RAJA::seq_exec>(RAJA::make_span(tmp.data(), N), Compose {}, seed);
+  RAJA::exclusive_scan_inplace<EXEC>(RAJA::make_span(din, N), Compose {}, seed);
+  EXPECT(to_host(din, N) == tmp);
+  cudaFree(din); cudaFree(dout);
+}
+
+template <class V> V make_val(long i) { return (V)i; }
+struct Val16 { long a; long b; bool operator==(const Val16& o) const { return a == o.a && b == o.b; } };
+template <> Val16 make_val<Val16>(long i) { return Val16 {i, ~i}; }
+struct Val12 { int a, b, c; bool operator==(const Val12& o) const { return a == o.a && b == o.b && c == o.c; } };  // 4-byte aligned, not a power of two
+template <> Val12 make_val<Val12>(long i) { return Val12 {(int)i, (int)(i * 3), (int)-i}; }
+struct Val8 { float a, b; bool operator==(const Val8& o) const { return a == o.a && b == o.b; } };  // 8 bytes, 4-byte aligned
+template <> Val8 make_val<Val8>(long i) { return Val8 {(float)i, (float)(i & 1023)}; }
+
+template <class K, class V = int> void test_sort(long N)
 {
   std::mt19937 gen(42 + (unsigned)N);
   std::vector<K> keys(N);
@@ -66,8 +104,8 @@ template <class K> void test_sort(long N)
     else k = (K)((long long)(gen() % (2 * N + 1)) - (std::is_signed<K>::value ? N : 0));
   }
   if (std::is_floating_point<K>::value && N > 4) { keys[1] = (K)0.0; keys[3] = (K)-0.0; }
-  std::vector<int> vals(N);
-  std::iota(vals.begin(), vals.end(), 0);
+  std::vector<V> vals(N);
+  for (long i = 0; i < N; ++i) vals[i] = make_val<V>(i);
   // keys only, ascending and descending
   {
     std::vector<K> ref = keys;
@@ -92,9 +130,9 @@ template <class K> void test_sort(long N)
   // pairs: stable, bit-exact keys AND values against stable_sort_pairs<seq_exec>
   for (int desc = 0; desc < 2; ++desc) {
     std::vector<K> rk = keys;
-    std::vector<int> rv = vals;
+    std::vector<V> rv = vals;
     K* dk = to_dev(keys);
-    int* dv = to_dev(vals);
+    V* dv = to_dev(vals);
     if (desc) {
       RAJA::stable_sort_pairs<RAJA::seq_exec>(RAJA::make_span(rk.data(), N), RAJA::make_span(rv.data(), N), RAJA::operators::greater<K> {});
       RAJA::stable_sort_pairs<EXEC>(RAJA::make_span(dk, N), RAJA::make_span(dv, N), RAJA::operators::greater<K> {});
@@ -159,6 +197,11 @@ int main()
     test_scan<long long, RAJA::operators::plus<long long>>(N, true);
     test_scan<double, RAJA::operators::plus<double>>(N, false);
     test_scan<float, RAJA::operators::maximum<float>>(N, true);
+    // element sizes outside 4 / 8 bytes (three-kernel scan of RAJA_b200/scan.hpp)
+    test_scan<short, RAJA::operators::plus<short>>(N, true);
+    test_scan<signed char, RAJA::operators::maximum<signed char>>(N, true);
+    test_scan<unsigned short, RAJA::operators::minimum<unsigned short>>(N, true);
+    test_scan_struct(N);
   }
   for (long N : {2L, 33L, 1000L, 9217L, 300007L}) {
     test_sort<int>(N);
@@ -166,6 +209,15 @@ int main()
     test_sort<long long>(N);
     test_sort<float>(N);
     test_sort<double>(N);
+    // 1- / 2-byte keys (widened) and values of other sizes (sorted by position, gathered)
+    test_sort<short>(N);
+    test_sort<unsigned short, short>(N);
+    test_sort<signed char, Val16>(N);
+    test_sort<unsigned char, unsigned char>(N);
+    test_sort<int, Val16>(N);
+    test_sort<double, Val12>(N);
+    test_sort<unsigned, Val8>(N);
+    test_sort<long long, short>(N);
   }
   test_atomics<int>(1000);
   test_atomics<unsigned>(1000);

@@ -50,7 +50,7 @@ int main(int argc, char** argv)
     printf("direct (1 index per thread, %ld blocks of 256)            : %8.4f ms\n", (n + 255) / 256, best);
   }
   const int sms = device_info().sm_count;
-  for (int per_sm : {1, 2, 3, 4, 6, 8, 16, 32}) {
+  for (int per_sm : {1, 2, 4, 8, 16, 32, 64, 128, 256, 512}) {
     const int g = sms * per_sm;
     printf("grid %5d (%2d/SM)  BLOCK 256:  UNROLL 1 %8.4f  2 %8.4f  4 %8.4f  8 %8.4f ms   | BLOCK 1024 UNROLL 1 %8.4f  4 %8.4f ms\n", g, per_sm, run<256, 1>(b, n, g), run<256, 2>(b, n, g),
            run<256, 4>(b, n, g), run<256, 8>(b, n, g), run<1024, 1>(b, n, g / 4 > 0 ? g / 4 : 1), run<1024, 4>(b, n, g / 4 > 0 ? g / 4 : 1));

@@ -60,19 +60,26 @@ elif a.path.startswith("scan"):
         x = torch.randint(0, 8, (n,), dtype=dt, device="cuda", generator=g)
     out = torch.empty_like(x)
     timed(lambda i: rb.inclusive_scan(x, out, pol=pol), 2 * x.element_size())
-elif a.path in ("sort", "sort_lowent", "sortf64"):
+elif a.path in ("sort", "sort_lowent", "sortf64", "sortu64", "sortf64u"):
     sets = []
     for i in range(a.reps + 1):
         if a.path == "sortf64":
             k = (torch.rand(n, dtype=torch.float64, device="cuda", generator=g) - 0.5) * 2e6
             sets.append((k, None))
+        elif a.path == "sortu64":  # every byte uniform
+            k = torch.randint(-2**63, 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+            sets.append((k.view(torch.uint64), None))
+        elif a.path == "sortf64u":  # fp64 keys whose bit patterns are uniform (finite, both signs, every exponent)
+            k = torch.randint(-2**63, 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+            k &= ~(1 << 62)  # exponent < 1024: no inf / nan
+            sets.append((k.view(torch.float64), None))
         else:
             k = torch.randint(-2**31, 2**31, (n,), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
             if a.path == "sort_lowent":
                 k &= 0xFF
             sets.append((k.view(torch.uint32), torch.arange(n, dtype=torch.int32, device="cuda").view(torch.uint32)))
     ka = torch.empty_like(sets[0][0])
-    if a.path == "sortf64":
+    if sets[0][1] is None:
         timed(lambda i: rb.stable_sort(sets[i][0], pol=pol), 136)
     else:
         va = torch.empty_like(sets[0][1])
