@@ -338,7 +338,7 @@ struct SweepShape {
   static_assert(LB_WARPS == 1 || LB_WARPS == 2, "");
   static_assert(LB_WARPS == 2 || MATCH_ >= 3, "the early-count kernel is written for two look-back warps");
   static constexpr int TILE = BLOCK * ITEMS;
-  static_assert(BLOCK % WARP == 0 && BLOCK >= RADIX, "one digit-owner thread per digit");
+  static_assert(BLOCK % WARP == 0 && BLOCK_ + LB_WARPS_ * WARP >= RADIX, "one digit-owner thread per digit (look-back warps take part in the late-count kernel)");
   static_assert(TILE < 65536, "tile-local counts must fit the look-back word next to its flags");
 };
 

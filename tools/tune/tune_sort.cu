@@ -126,7 +126,17 @@ int main(int argc, char** argv)
            CUB_VERSION, best, b.n / best / 1e6, MODEL_BYTES, MODEL_BYTES * b.n / best / 1e6);
     cudaFree(tmp);
   }
-#if TK == 0
+#if TK == 0 && defined(SMALL_CTAS)
+  // r02: more, smaller CTAs per SM (the sweep is bound by neither pipe alone: LSU 76 %, ALU 61 %, issue 54 % -- do more phases in flight help?)
+  run_shape<rsort::SweepShape<256, 32, 3, 3, false, 300, 2, 2>>(b);
+  run_shape<rsort::SweepShape<192, 32, 4, 3, false, 400, 2, 2>>(b);
+  run_shape<rsort::SweepShape<192, 28, 4, 3, false, 400, 2, 2>>(b);
+  run_shape<rsort::SweepShape<192, 32, 4, 3, false, 600, 2, 2>>(b);
+  run_shape<rsort::SweepShape<192, 32, 4, 3, false, 400, 2, 2, 400, 12>>(b);
+  run_shape<rsort::SweepShape<192, 30, 4, 3, false, 400, 2, 2>>(b);
+  run_shape<rsort::SweepShape<192, 24, 5, 3, false, 500, 2, 2>>(b);
+  run_shape<rsort::SweepShape<224, 32, 3, 3, false, 300, 2, 2>>(b);
+#elif TK == 0
   // r02: larger tiles at 2 CTAs per SM (what paid for the 64-bit keys)
   run_shape<rsort::SweepShape<256, 32, 3, 3, false, 300, 2, 2>>(b);
   run_shape<rsort::SweepShape<256, 40, 2, 3, false, 200, 2, 2>>(b);
