@@ -105,10 +105,18 @@ template <bool FLOAT, class U> B200_D unsigned sweep_digit(U k, int shift, unsig
 // made this kernel LSU-bound at 2.5 TB/s).  One persistent CTA per SM, 128 KB of counters.
 template <class U> struct HistShape {
   static constexpr int NPASS = sizeof(U);
-  static constexpr int COLS = sizeof(U) == 4 ? 32 : 16;
+  // 4-byte keys: 32 columns, lane = column, every lane counts all four digit positions of its own keys.
+  // 8-byte keys: eight digit positions x 256 bins x 32 columns do not fit; with 16 columns two lanes shared a column and half of
+  // the atomics met a two-way bank conflict (0.55 ms for 2^28 keys, LSU-bound).  Now the two half-warps split the PASSES of the
+  // same keys: lanes 0-15 count the even digit positions, lanes 16-31 the odd ones, and the parity of the pass selects the half
+  // of the banks -- every atomic of a warp hits 32 distinct banks again.
+  static constexpr bool SPLIT = sizeof(U) == 8;
+  static constexpr int COLS = SPLIT ? 16 : 32;
   static constexpr int BLOCK = 1024;
   static constexpr int VEC = 16 / sizeof(U);  // keys per 128-bit load
   static constexpr int SMEM = NPASS * RADIX * COLS * 4;
+  // counter of (pass p, digit d), column c
+  B200_HD static int slot(int p, int d, int c) { return SPLIT ? ((((p >> 1) * RADIX + d) * 2 + (p & 1)) * COLS + c) : ((p * RADIX + d) * COLS + c); }
 };
 
 template <class U>
@@ -118,12 +126,14 @@ histogram_kernel(const U* __restrict__ keys, const long long n, unsigned long lo
 {
   using H = HistShape<U>;
   constexpr int NPASS = H::NPASS, COLS = H::COLS, BLOCK = H::BLOCK, VEC = H::VEC;
+  constexpr bool SPLIT = H::SPLIT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* const sh = reinterpret_cast<uint32_t*>(smem_raw);  // [NPASS][RADIX][COLS]
+  uint32_t* const sh = reinterpret_cast<uint32_t*>(smem_raw);  // H::slot(pass, digit, column)
   for (int i = threadIdx.x; i < NPASS * RADIX * COLS; i += BLOCK) sh[i] = 0;
   __syncthreads();
 
-  uint32_t* const col = sh + (threadIdx.x & (COLS - 1));
+  const int hw = SPLIT ? ((threadIdx.x >> 4) & 1) : 0;  // SPLIT: which passes this lane counts (2 q + hw)
+  uint32_t* const col = sh + (threadIdx.x & (COLS - 1)) + hw * COLS;
   // The order-preserving map is an XOR with one constant for integer keys (floating keys first flip the magnitude bits
   // of negatives and rank -0.0 as +0.0, as sweep_digit does), and a digit is ONE byte-permute: per key 1 + NPASS x
   // (PRMT, LEA, ATOMS) instructions instead of the ~20 a run-time KeyOrder switch and shift/mask pairs cost -- the kernel
@@ -145,41 +155,55 @@ histogram_kernel(const U* __restrict__ keys, const long long n, unsigned long lo
         k ^= (U)((SU)k >> (BITS - 1)) & ~SIGN;
       }
       const U ok = k ^ xmask;
+      if constexpr (SPLIT) {
+        const uint32_t lo = (uint32_t)ok, hi = (uint32_t)(ok >> (BITS > 32 ? 32 : 0));
+        const uint32_t sel0 = 0x4440u | (uint32_t)hw, sel1 = 0x4440u | (uint32_t)(2 + hw);
+        // passes hw, 2 + hw (low word) and 4 + hw, 6 + hw (high word): q = 0 .. 3
+        atomicAdd(col + (0 * RADIX + (int)__byte_perm(lo, 0u, sel0)) * (2 * COLS), 1u);
+        atomicAdd(col + (1 * RADIX + (int)__byte_perm(lo, 0u, sel1)) * (2 * COLS), 1u);
+        atomicAdd(col + (2 * RADIX + (int)__byte_perm(hi, 0u, sel0)) * (2 * COLS), 1u);
+        atomicAdd(col + (3 * RADIX + (int)__byte_perm(hi, 0u, sel1)) * (2 * COLS), 1u);
+      } else {
 #pragma unroll
-      for (int p = 0; p < NPASS; ++p) {
-        const uint32_t half = (uint32_t)(p < 4 ? ok : (ok >> (BITS > 32 ? 32 : 0)));
-        const uint32_t d = __byte_perm(half, 0u, 0x4440u | (uint32_t)(p & 3));
-        atomicAdd(col + (p * RADIX + (int)d) * COLS, 1u);
+        for (int p = 0; p < NPASS; ++p) {
+          const uint32_t half = (uint32_t)(p < 4 ? ok : (ok >> (BITS > 32 ? 32 : 0)));
+          const uint32_t d = __byte_perm(half, 0u, 0x4440u | (uint32_t)(p & 3));
+          atomicAdd(col + (p * RADIX + (int)d) * COLS, 1u);
+        }
       }
     };
-    // 128-bit loads over the aligned body; a CTA sees < 2^32 keys, so the 32-bit counters cannot overflow
+    // 128-bit loads over the aligned body; a CTA sees < 2^32 keys, so the 32-bit counters cannot overflow.
+    // SPLIT: the two half-warps load the SAME vectors (lane l and l + 16 one address: one L1 request serves both), so a block
+    // covers BLOCK / 2 vectors per load instruction.
+    constexpr int LANES = SPLIT ? BLOCK / 2 : BLOCK;  // distinct vectors per block and load instruction
+    const int vt = SPLIT ? (int)((threadIdx.x >> 5) * 16 + (threadIdx.x & 15)) : (int)threadIdx.x;
     const uintptr_t addr = (uintptr_t)keys;
     long long head = (long long)(((16 - (addr & 15)) & 15) / sizeof(U));
     if (head > n) head = n;
     const long long nvec = (n - head) / VEC;
     using V = Vec<U, VEC>;
     const V* const body = reinterpret_cast<const V*>(keys + head);
-    constexpr int UNROLL = 4;
-    long long v = (long long)blockIdx.x * BLOCK * UNROLL + threadIdx.x;
-    const long long stride = (long long)gridDim.x * BLOCK * UNROLL;
-    for (; v + (UNROLL - 1) * BLOCK < nvec; v += stride) {
+    constexpr int UNROLL = SPLIT ? 8 : 4;
+    long long v = (long long)blockIdx.x * LANES * UNROLL + vt;
+    const long long stride = (long long)gridDim.x * LANES * UNROLL;
+    for (; v + (UNROLL - 1) * LANES < nvec; v += stride) {
       V x[UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) x[u] = ld_stream(body + v + u * BLOCK);
+      for (int u = 0; u < UNROLL; ++u) x[u] = ld_stream(body + v + u * LANES);
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
         for (int e = 0; e < VEC; ++e) count(x[u].e[e]);
     }
     for (int u = 0; u < UNROLL; ++u)
-      if (v + u * BLOCK < nvec) {
-        const V x = ld_stream(body + v + u * BLOCK);
+      if (v + u * LANES < nvec) {
+        const V x = ld_stream(body + v + u * LANES);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) count(x.e[e]);
       }
-    if (blockIdx.x == 0) {  // unaligned head and the tail shorter than one vector
-      for (long long i = threadIdx.x; i < head; i += BLOCK) count(keys[i]);
-      for (long long i = head + nvec * VEC + threadIdx.x; i < n; i += BLOCK) count(keys[i]);
+    if (blockIdx.x == 0) {  // unaligned head and the tail shorter than one vector (SPLIT: both half-warps see every such key)
+      for (long long i = vt; i < head; i += LANES) count(keys[i]);
+      for (long long i = head + nvec * VEC + vt; i < n; i += LANES) count(keys[i]);
     }
   };
   if (order.kind == KEY_FLOAT) run(std::true_type{});
@@ -189,7 +213,7 @@ histogram_kernel(const U* __restrict__ keys, const long long n, unsigned long lo
   for (int b = threadIdx.x; b < NPASS * RADIX; b += BLOCK) {
     uint32_t c = 0;
 #pragma unroll
-    for (int k = 0; k < COLS; ++k) c += sh[b * COLS + ((k + threadIdx.x) & (COLS - 1))];  // rotated: conflict-free
+    for (int k = 0; k < COLS; ++k) c += sh[H::slot(b / RADIX, b % RADIX, (k + threadIdx.x) & (COLS - 1))];  // rotated: conflict-free
     if (c) atomicAdd(ghist + b, (unsigned long long)c);
   }
 }

@@ -291,17 +291,19 @@ int run_reduce_atomic(cudaStream_t stream, Body body, Index len, typename Op::va
   return 0;
 }
 
+// reducer-free streaming bodies: oversubscribed grid, as the policy layer launches user lambdas (b200/forall.cuh: persistent_grid)
+constexpr int STREAM_WAVES = 32;
 template <class T> int triad_t(T* a, const T* b, const T* c, double s, Index n, cudaStream_t st)
 {
   constexpr int V = 16 / sizeof(T);
   if (aligned16(a) && aligned16(b) && aligned16(c)) {
     VecSpace<T, V> sp(n);
     TriadBody<T, V> body{a, b, c, (T)s, sp.nv, n};
-    const int grid = forall_grid<BLOCK, 4, Index, TriadBody<T, V>, NoFinalize>(sp.nv);
+    const int grid = forall_grid<BLOCK, 4, Index, TriadBody<T, V>, NoFinalize>(sp.nv, 0, STREAM_WAVES);
     RB200_CUDA((launch_forall<BLOCK, 4, Index>(st, body, sp.nv, NoFinalize{}, grid)));
   } else {
     TriadBody<T, 1> body{a, b, c, (T)s, n, n};
-    const int grid = forall_grid<BLOCK, 8, Index, TriadBody<T, 1>, NoFinalize>(n);
+    const int grid = forall_grid<BLOCK, 8, Index, TriadBody<T, 1>, NoFinalize>(n, 0, STREAM_WAVES);
     RB200_CUDA((launch_forall<BLOCK, 8, Index>(st, body, n, NoFinalize{}, grid)));
   }
   return 0;
@@ -313,11 +315,11 @@ template <class T> int daxpy_t(T* a, const T* b, double s, Index n, cudaStream_t
   if (aligned16(a) && aligned16(b)) {
     VecSpace<T, V> sp(n);
     DaxpyBody<T, V> body{a, b, (T)s, sp.nv, n};
-    const int grid = forall_grid<BLOCK, 4, Index, DaxpyBody<T, V>, NoFinalize>(sp.nv);
+    const int grid = forall_grid<BLOCK, 4, Index, DaxpyBody<T, V>, NoFinalize>(sp.nv, 0, STREAM_WAVES);
     RB200_CUDA((launch_forall<BLOCK, 4, Index>(st, body, sp.nv, NoFinalize{}, grid)));
   } else {
     DaxpyBody<T, 1> body{a, b, (T)s, n, n};
-    const int grid = forall_grid<BLOCK, 8, Index, DaxpyBody<T, 1>, NoFinalize>(n);
+    const int grid = forall_grid<BLOCK, 8, Index, DaxpyBody<T, 1>, NoFinalize>(n, 0, STREAM_WAVES);
     RB200_CUDA((launch_forall<BLOCK, 8, Index>(st, body, n, NoFinalize{}, grid)));
   }
   return 0;
