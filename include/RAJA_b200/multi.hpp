@@ -16,6 +16,7 @@
 //   reducer parameters  grid reduce per GPU -> all-gather of the scalars through peer memory -> folded in rank order into the
 //                       target on every rank (deterministic; MinLoc / MaxLoc keep the first extremum: ranks own ascending ranges)
 //   scans               shard total -> exclusive prefix over the ranks (one peer-memory kernel) -> scan seeded with that carry
+//                       (a rank whose shard may be EMPTY calls RAJA::b200::multi_inclusive_scan / multi_exclusive_scan below)
 //   sort_pairs          sample sort: regular sample of the unsorted shard, splitters selected on the device, ONE sweep that writes
 //                       every bucket straight into its destination GPU (fused partition + all-to-all), one local onesweep sort
 // The exchanges use the peer-memory communicator of libraja_b200.so (include/raja_b200.h, rb200_comm_*): `workspaces` are the
@@ -148,6 +149,21 @@ template<typename K>
 inline SortedPiece<K, unsigned> multi_sort(MultiResource& m, const K* keys, long long n, bool descending = false)
 {
   return multi_sort_pairs<K, unsigned>(m, keys, nullptr, n, descending);
+}
+
+//! Collective scans that are safe for EMPTY shards.  RAJA::inclusive_scan<b200_multi_exec>(...) & co. work as long as every rank's
+//! shard holds at least one element: RAJA's front-end returns before it reaches any back-end when the range is empty
+//! (pattern/scan.hpp:72, 137, 212, 291), so a rank with an empty shard would skip the carry exchange its peers are waiting in.
+//! These entry points go to the back-end directly; in place (out == in) is fine.  Collective: every rank calls them.
+template<typename T, typename Function>
+inline void multi_inclusive_scan(MultiResource& m, const T* in, T* out, long long n, Function op)
+{
+  ::RAJA::impl::scan::b200_detail::run_multi<true, false>(m.resource(), in, in + n, out, op, T {});
+}
+template<typename T, typename Function>
+inline void multi_exclusive_scan(MultiResource& m, const T* in, T* out, long long n, Function op, T init)
+{
+  ::RAJA::impl::scan::b200_detail::run_multi<false, false>(m.resource(), in, in + n, out, op, init);
 }
 
 //! Ranks that are host threads of ONE process: every thread sets its device, then attach()es -- allocates its workspace, enables

@@ -139,6 +139,16 @@ int rb200_comm_create(int rank, int world, void* const* ws_ptrs, size_t ws_bytes
     delete c;
     return cuda_fail(e, "cudaMemset(comm header)");
   }
+  // Pinned staging blocks (count matrices, reducer results: all in the smallest size class) are taken from the pinned pool
+  // between collectives; a pool miss there is a cudaHostAlloc, which synchronises with every device of the process -- and a
+  // peer device may be spinning in an exchange kernel that waits for this rank (ranks as threads of one process).  Stock the
+  // pool now, while the ranks are still being set up (the caller synchronises them after this call).
+  {
+    void* warm[8];
+    for (void*& w : warm) w = rb200::pool_malloc(rb200::POOL_PINNED, 512, nullptr);
+    for (void* w : warm)
+      if (w) rb200::pool_free(rb200::POOL_PINNED, w, nullptr);
+  }
   *out = c;
   return 0;
 }

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <random>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 
 static std::mutex g_mu;
@@ -22,8 +23,18 @@ static int g_fail = 0;
   } while (0)
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
 
-template <class T> T* to_dev(const T* h, size_t n) { T* p; CK(cudaMalloc(&p, n * sizeof(T) + 64)); CK(cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice)); return p; }
-template <class T> std::vector<T> to_host(const T* d, size_t n) { std::vector<T> h(n); if (n) CK(cudaMemcpy(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost)); return h; }
+// Every copy of a rank goes through the rank's OWN stream: the synchronous cudaMemcpy / cudaMemset run on the legacy default
+// stream, which waits for all blocking streams of the device -- with several ranks on one device (RB200_OVERSUBSCRIBE) that is
+// another rank's exchange kernel, spinning until THIS rank arrives.
+static thread_local cudaStream_t tl_stream = nullptr;
+static void copy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind)
+{
+  if (!bytes) return;
+  CK(cudaMemcpyAsync(dst, src, bytes, kind, tl_stream));
+  CK(cudaStreamSynchronize(tl_stream));
+}
+template <class T> T* to_dev(const T* h, size_t n) { T* p; CK(cudaMalloc(&p, n * sizeof(T) + 64)); copy_sync(p, h, n * sizeof(T), cudaMemcpyHostToDevice); return p; }
+template <class T> std::vector<T> to_host(const T* d, size_t n) { std::vector<T> h(n); copy_sync(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost); return h; }
 
 using MEXEC = RAJA::b200_multi_exec<256>;
 
@@ -41,6 +52,7 @@ static void rank_main(int rank, int world, RAJA::b200::LocalPeerGroup* group, Co
   // another device brings its own stream (camp::resources::Cuda::CudaFromStream, tpl/camp/include/camp/resource/cuda.hpp:140-146)
   cudaStream_t stream;
   CK(cudaStreamCreate(&stream));
+  tl_stream = stream;
   RAJA::resources::Cuda res = RAJA::resources::Cuda::CudaFromStream(stream);
   RAJA::b200::MultiResource mres(rank, world, ptrs, group->bytes(), res);
 
@@ -57,6 +69,30 @@ static void rank_main(int rank, int world, RAJA::b200::LocalPeerGroup* group, Co
   double* dd     = to_dev(gd.data() + lo, (size_t)n);
   RAJA::b200::ShardedSpan<int, long> a(di, lo);
   RAJA::b200::ShardedSpan<double, long> x(dd, lo);
+  // Ranks are threads of ONE process: cudaMalloc / cudaFree of memory that is mapped into the peers may have to wait for the peer
+  // devices, and a peer device may be running an exchange kernel that waits for THIS rank -- a rank that allocates or frees between
+  // two collectives can deadlock the group (seen at world 8: the 10 s trap of the waiting kernel).  So: every buffer is allocated
+  // before the first collective and freed after the last one, with a host rendezvous on both sides, and the stream-ordered pools
+  // (the library's scratch) are warmed by rank-local calls of the same sizes.  (One process per GPU has none of this.)
+  double* out; CK(cudaMalloc(&out, (size_t)n * 8 + 64));
+  int* so; CK(cudaMalloc(&so, (size_t)n * 4 + 64));
+  double* dob; CK(cudaMalloc(&dob, (size_t)n * 8 + 64));
+  unsigned* dk; CK(cudaMalloc(&dk, (size_t)n * 4 + 64));
+  unsigned* dv; CK(cudaMalloc(&dv, (size_t)n * 4 + 64));
+  double* df; CK(cudaMalloc(&df, (size_t)n * 8 + 64));
+  if (n > 0) {  // warm-up: local scan / sorts / reduction of the shard's size on this rank's stream
+    using LEXEC = RAJA::b200_exec<256>;
+    CK(cudaMemsetAsync(dk, 1, (size_t)n * 4, stream)); CK(cudaMemsetAsync(dv, 2, (size_t)n * 4, stream)); CK(cudaMemsetAsync(df, 3, (size_t)n * 8, stream));
+    RAJA::inclusive_scan<LEXEC>(res, RAJA::make_span(di, n), RAJA::make_span(so, n), RAJA::operators::plus<int> {});
+    RAJA::inclusive_scan<LEXEC>(res, RAJA::make_span(dd, n), RAJA::make_span(dob, n), RAJA::operators::plus<double> {});
+    RAJA::sort_pairs<LEXEC>(res, RAJA::make_span(dk, n), RAJA::make_span(dv, n));
+    RAJA::sort<LEXEC>(res, RAJA::make_span(df, n));
+    long wsum = 0;
+    RAJA::forall<LEXEC>(res, RAJA::TypedRangeSegment<long>(0, n), RAJA::expt::Reduce<RAJA::operators::plus>(&wsum),
+                        [=] RAJA_DEVICE(long i, RAJA::expt::ValOp<long, RAJA::operators::plus>& s_) { s_ += di[i]; });
+  }
+  res.wait();
+  group->rendezvous();
 
   // ---- forall + reducer parameters across ranks
   {
@@ -84,44 +120,42 @@ static void rank_main(int rank, int world, RAJA::b200::LocalPeerGroup* group, Co
   }
   // ---- a plain sharded forall (no exchange): triad on the shard with global indices
   {
-    double* out; CK(cudaMalloc(&out, (size_t)n * 8 + 64));
     RAJA::b200::ShardedSpan<double, long> o(out, lo);
     RAJA::forall<MEXEC>(mres.resource(), seg, [=] RAJA_DEVICE(long i) { o[i] = x[i] + 3.0 * (double)i; });
     auto h = to_host(out, (size_t)n);
     bool ok = true;
     for (long i = 0; i < n; ++i) ok = ok && (h[i] == gd[lo + i] + 3.0 * (double)(lo + i));
     EXPECT(ok);
-    cudaFree(out);
   }
   // ---- scans with the carry exchanged between ranks
   {
-    int* so; CK(cudaMalloc(&so, (size_t)n * 4 + 64));
     std::vector<int> ref(N);
     RAJA::inclusive_scan<RAJA::seq_exec>(RAJA::make_span(gi.data(), N), RAJA::make_span(ref.data(), N), RAJA::operators::plus<int> {});
-    RAJA::inclusive_scan<MEXEC>(mres.resource(), RAJA::make_span(di, n), RAJA::make_span(so, n), RAJA::operators::plus<int> {});
+    // RAJA's front-end returns early on an empty range (pattern/scan.hpp:72): a rank with an empty shard uses the collective entry point
+    if (n > 0) RAJA::inclusive_scan<MEXEC>(mres.resource(), RAJA::make_span(di, n), RAJA::make_span(so, n), RAJA::operators::plus<int> {});
+    else RAJA::b200::multi_inclusive_scan(mres, di, so, n, RAJA::operators::plus<int> {});
     EXPECT(to_host(so, (size_t)n) == std::vector<int>(ref.begin() + lo, ref.begin() + lo + n));
     RAJA::exclusive_scan<RAJA::seq_exec>(RAJA::make_span(gi.data(), N), RAJA::make_span(ref.data(), N), RAJA::operators::minimum<int> {}, 77);
-    RAJA::exclusive_scan<MEXEC>(mres.resource(), RAJA::make_span(di, n), RAJA::make_span(so, n), RAJA::operators::minimum<int> {}, 77);
+    if (n > 0) RAJA::exclusive_scan<MEXEC>(mres.resource(), RAJA::make_span(di, n), RAJA::make_span(so, n), RAJA::operators::minimum<int> {}, 77);
+    else RAJA::b200::multi_exclusive_scan(mres, di, so, n, RAJA::operators::minimum<int> {}, 77);
     EXPECT(to_host(so, (size_t)n) == std::vector<int>(ref.begin() + lo, ref.begin() + lo + n));
-    cudaFree(so);
-    double* dob; CK(cudaMalloc(&dob, (size_t)n * 8 + 64));
-    CK(cudaMemcpy(dob, dd, (size_t)n * 8, cudaMemcpyDeviceToDevice));
+    copy_sync(dob, dd, (size_t)n * 8, cudaMemcpyDeviceToDevice);
     std::vector<double> rd(gd);
     RAJA::inclusive_scan_inplace<RAJA::seq_exec>(RAJA::make_span(rd.data(), N), RAJA::operators::plus<double> {});
-    RAJA::inclusive_scan_inplace<MEXEC>(mres.resource(), RAJA::make_span(dob, n), RAJA::operators::plus<double> {});
+    if (n > 0) RAJA::inclusive_scan_inplace<MEXEC>(mres.resource(), RAJA::make_span(dob, n), RAJA::operators::plus<double> {});
+    else RAJA::b200::multi_inclusive_scan(mres, dob, dob, n, RAJA::operators::plus<double> {});
     auto h = to_host(dob, (size_t)n);
     bool ok = true;
     for (long i = 0; i < n; ++i) ok = ok && (std::fabs(h[i] - rd[lo + i]) <= N * 2.3e-16 * rd[N - 1]);
     EXPECT(ok);
-    cudaFree(dob);
   }
   // ---- sample sort across ranks: u32 keys (every third key from a 256-value alphabet: long runs of duplicates that straddle
   //      ranks) + the global index as value; fp64 keys only, descending
   {
     std::vector<unsigned> gk(N), gv(N);
     for (long i = 0; i < N; ++i) { gk[i] = (i % 3 == 0) ? (gen() & 0xffu) : gen(); gv[i] = (unsigned)i; }
-    unsigned* dk = to_dev(gk.data() + lo, (size_t)n);
-    unsigned* dv = to_dev(gv.data() + lo, (size_t)n);
+    copy_sync(dk, gk.data() + lo, (size_t)n * 4, cudaMemcpyHostToDevice);
+    copy_sync(dv, gv.data() + lo, (size_t)n * 4, cudaMemcpyHostToDevice);
     auto piece = RAJA::b200::multi_sort_pairs(mres, dk, dv, (long long)n);
     mres.resource().wait();
     col->k32[rank] = to_host(piece.keys, (size_t)piece.n);
@@ -134,10 +168,9 @@ static void rank_main(int rank, int world, RAJA::b200::LocalPeerGroup* group, Co
       EXPECT(ak == gk); EXPECT(av == gv);
     }
     group->rendezvous();
-    cudaFree(dk); cudaFree(dv);
     std::vector<double> gf(N);
     for (long i = 0; i < N; ++i) gf[i] = ((gen() % 2000001) - 1000000.0) * (i % 7 == 0 ? 0.0 : 1.0) * (i % 11 == 0 ? -1.0 : 1.0);
-    double* df = to_dev(gf.data() + lo, (size_t)n);
+    copy_sync(df, gf.data() + lo, (size_t)n * 8, cudaMemcpyHostToDevice);
     auto pf = RAJA::b200::multi_sort(mres, df, (long long)n, /*descending=*/true);
     mres.resource().wait();
     col->f64[rank] = to_host(pf.keys, (size_t)pf.n);
@@ -152,11 +185,11 @@ static void rank_main(int rank, int world, RAJA::b200::LocalPeerGroup* group, Co
       EXPECT(ok);
     }
     group->rendezvous();
-    cudaFree(df);
   }
   mres.barrier();
   mres.resource().wait();
-  cudaFree(di); cudaFree(dd);
+  group->rendezvous();  // nobody frees while a peer may still be inside a collective
+  cudaFree(di); cudaFree(dd); cudaFree(out); cudaFree(so); cudaFree(dob); cudaFree(dk); cudaFree(dv); cudaFree(df);
   group->rendezvous();
 }
 
@@ -171,13 +204,26 @@ int main(int argc, char** argv)
   CK(cudaGetDeviceCount(&ndev));
   int world = ndev < 8 ? ndev : 8;
   if (const char* w = getenv("RB200_WORLD")) world = atoi(w);
-  if (world < 1 || world > ndev) { printf("test_multi: world %d needs that many devices (%d visible)\n", world, ndev); return 2; }
-  for (long N : {1000003L, 5L, 40000L}) {  // 5 elements over up to 8 ranks: empty shards
+  // RB200_OVERSUBSCRIBE=1: more ranks than devices (rank r runs on device r % ndev; ranks that share a device exchange through plain
+  // device memory) -- the world-8 logic (seven splitters, empty shards) on a smaller box
+  if (world < 1 || (world > ndev && !getenv("RB200_OVERSUBSCRIBE"))) { printf("test_multi: world %d needs that many devices (%d visible)\n", world, ndev); return 2; }
+  std::vector<long> sizes = {1000003L, 5L, 40000L};  // 5 elements over up to 8 ranks: empty shards
+  if (const char* one = getenv("RB200_TEST_N")) sizes = {atol(one)};
+  for (long N : sizes) {
     RAJA::b200::LocalPeerGroup group(world, RAJA::b200::MultiResource::workspace_bytes((size_t)(N / world + 1) * 3 + 65536, 8, 4));
     Collect col;
     col.k32.resize(world); col.v32.resize(world); col.f64.resize(world);
     std::vector<std::thread> th;
-    for (int r = 0; r < world; ++r) th.emplace_back(rank_main, r, world, &group, &col, N);
+    for (int r = 0; r < world; ++r)
+      th.emplace_back([&, r] {
+        try {
+          rank_main(r, world, &group, &col, N);
+        } catch (const std::exception& e) {  // say what failed before the process goes down (the other ranks are waiting for this one)
+          printf("test_multi: rank %d of %d, N = %ld: exception: %s\n", r, world, N, e.what());
+          fflush(stdout);
+          _exit(3);
+        }
+      });
     for (auto& t : th) t.join();
     printf("test_multi: N = %ld world = %d: %s\n", N, world, g_fail ? "FAILED" : "ok");
   }
