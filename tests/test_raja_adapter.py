@@ -32,3 +32,17 @@ def test_adapter_parity_on_gpu(prog):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert ": OK" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [3, 8])
+def test_multi_policy_world_logic_on_one_gpu(world):
+    """The C++ multi-GPU policy with MORE ranks than devices (ranks are host threads, rank r on device r % ndev): the world-3 / world-8
+    logic -- seven splitters, shards of different lengths, EMPTY shards (5 elements over 8 ranks), peer exchanges -- runs on whatever
+    the box has; on real 8 GPUs the same program runs one rank per device (profiles/r02_test_multi_cpp.txt)."""
+    exe = os.path.join(BUILD, "test_multi")
+    assert os.path.exists(exe), f"{exe} missing (built by __graft_entry__.build() in the build container)"
+    env = dict(os.environ, RB200_OVERSUBSCRIBE="1", RB200_WORLD=str(world))
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert f"OK (world = {world})" in r.stdout
